@@ -1,0 +1,71 @@
+"""ctypes binding of libgnnome_b200.so (the C ABI in include/gnnome_b200.h).
+
+The product path has NO fallback: if the library is missing, `lib()` raises.  `lib()` only loads the
+shared object (works on a CPU-only box, used by the symbol-export test); compute entry points need a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnnome_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); mirrors include/gnnome_b200.h one to one
+SIGNATURES = {
+    "gg_version": (_i, []),
+    "gg_last_error": (C.c_char_p, []),
+    "gg_plan_create": (_i, [_p, _p, _i64, _i64, _p, C.POINTER(_p)]),
+    "gg_plan_destroy": (_i, [_p]),
+    "gg_plan_num_nodes": (_i64, [_p]),
+    "gg_plan_num_edges": (_i64, [_p]),
+    "gg_plan_perm": (_p, [_p]),
+    "gg_plan_inv_perm": (_p, [_p]),
+    "gg_plan_src": (_p, [_p]),
+    "gg_plan_dst": (_p, [_p]),
+    "gg_plan_in_ptr": (_p, [_p]),
+    "gg_plan_out_ptr": (_p, [_p]),
+    "gg_plan_out_eid": (_p, [_p]),
+    "gg_plan_copy_array": (_i, [_p, _i, _p, _p]),
+    "gg_linear_fwd": (_i, [_i64, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "gg_linear_bwd_data": (_i, [_i64, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "gg_linear_bwd_weight": (_i, [_i64, _i, _i, _p, _p, _p, _p, _p]),
+    "gg_layer_fwd": (_i, [_p, _i, _i, _i] + [_p] * 18),
+    "gg_layer_bwd": (_i, [_p, _i, _i, _i] + [_p] * 32),
+    "gg_score_fwd": (_i, [_p, _i, _i] + [_p] * 11),
+    "gg_score_bwd": (_i, [_p, _i, _i] + [_p] * 18),
+    "gg_gather_rows": (_i, [_i64, _i, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"gnnome_assembly_b200: {LIB_PATH} is missing — build it with "
+                "`python -m gnnome_assembly_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)        # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gg_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

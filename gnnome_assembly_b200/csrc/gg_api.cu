@@ -1,0 +1,359 @@
+// gg_api.cu — C ABI entry points (include/gnnome_b200.h): dense linear, GatedGCN layer forward /
+// backward, edge score predictor forward / backward.  Host code only sequences kernel launches on the
+// caller's stream; every buffer is caller-owned.
+#include "gg_common.cuh"
+#include "gg_gemm_ffma.cuh"
+#include "gg_layer_kernels.cuh"
+
+namespace gg {
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// one warp per node, 8 warps per CTA, at most 8 CTAs resident per SM (grid-stride beyond that)
+static unsigned node_grid(int64_t n) {
+  int64_t blocks = (n + (kNodeThreads / 32) - 1) / (kNodeThreads / 32);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+static int pick_splits(int64_t K, int64_t tiles) {
+  int64_t want = (2LL * sm_count() + tiles - 1) / tiles;
+  int64_t max_by_k = (K + 511) / 512;          // at least 512 reduction rows per split
+  if (want > max_by_k) want = max_by_k;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+// ------------------------------------------------------------------ generic GEMM front-ends
+// Y[M,N] = X[M,K] W[N,K]^T (+b)(relu)
+static int linear_fwd(int64_t M, int N, int K, const float* X, int64_t ldx, const float* W, int64_t ldw,
+                      const float* b, int relu, float* Y, int64_t ldy, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = X; g.lda = ldx; g.B = W; g.ldb = ldw; g.M = M; g.N = N; g.K = K;
+  EpiBias epi{Y, ldy, b, relu};
+  if (N >= 128) return launch_gemm<128, false, true, false, false>(g, epi, 1, st);
+  if (N > 32) return launch_gemm<64, false, true, false, false>(g, epi, 1, st);
+  return launch_gemm<32, false, true, false, false>(g, epi, 1, st);
+}
+
+// dX[M,K] = dY[M,N] W[N,K] (+addend)(mask)
+static int linear_bwd_data(int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
+                           const float* addend, const float* mask, float* dX, int64_t lddx, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dY; g.lda = lddy; g.B = W; g.ldb = ldw; g.M = M; g.N = K; g.K = N;
+  EpiAddMask epi{dX, lddx, addend, mask};
+  if (K >= 128) return launch_gemm<128, false, false, false, false>(g, epi, 1, st);
+  if (K > 32) return launch_gemm<64, false, false, false, false>(g, epi, 1, st);
+  return launch_gemm<32, false, false, false, false>(g, epi, 1, st);
+}
+
+// dW[N,K] = dY[M,N]^T X[M,K] ; db[N] = colsum(dY)       (dW, db zeroed here)
+static int linear_bwd_weight(int64_t M, int N, int K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
+                             float* dW, float* db, cudaStream_t st) {
+  GG_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
+  if (db) GG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+  if (M <= 0) return GG_OK;
+  GemmArgs g{};
+  g.A = dY; g.lda = lddy; g.B = X; g.ldb = ldx; g.M = N; g.N = K; g.K = M;
+  g.bias_grad = db;
+  EpiAtomic epi{dW, (int64_t)K};
+  const int64_t m_tiles = (N + kBM - 1) / kBM;
+  if (K >= 128) return launch_gemm<128, true, false, false, true>(g, epi, pick_splits(M, m_tiles * ((K + 127) / 128)), st);
+  if (K > 32) return launch_gemm<64, true, false, false, true>(g, epi, pick_splits(M, m_tiles), st);
+  return launch_gemm<32, true, false, false, true>(g, epi, pick_splits(M, m_tiles), st);
+}
+
+// ------------------------------------------------------------------ layer forward / backward
+template <int D, int NORM>
+static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const float* e_in, const float* Wn,
+                          const float* bn, const float* B3, const float* b3, const float* gamma_e,
+                          const float* beta_e, const float* gamma_h, const float* beta_h, float* h_out,
+                          float* e_out, float* P, float* t, float* z, float* agg, double* stats, cudaStream_t st) {
+  const int64_t N = pl->N, E = pl->E;
+  GG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * D, st));
+  // node projections P = h [A1|A2|A3|B1|B2]^T + b      (gated_gcn_full.py:107-112)
+  int rc = linear_fwd(N, 5 * D, D, h_in, D, Wn, D, bn, 0, P, 5 * D, st);
+  if (rc) return rc;
+  // t = B3 e + b3 + B1h[src] + B2h[dst], with batch statistics  (:113,120-121)
+  {
+    GemmArgs g{};
+    g.A = e_in; g.lda = D; g.B = B3; g.ldb = D; g.M = E; g.N = D; g.K = D;
+    g.col_stats = stats;
+    EpiEdgeGate epi{t, D, b3, P, pl->src, pl->dst};
+    constexpr int BN = D >= 128 ? 128 : 64;
+    rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>(g, epi, 1, st);
+    if (rc) return rc;
+  }
+  edge_gate_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+      N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
+  GG_LAUNCH_CHECK("edge_gate_fwd_kernel");
+  node_agg_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+      N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D);
+  GG_LAUNCH_CHECK("node_agg_fwd_kernel");
+  node_update_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+      N, z, h_in, stats + 2 * D, gamma_h, beta_h, residual, h_out);
+  GG_LAUNCH_CHECK("node_update_fwd_kernel");
+  return GG_OK;
+}
+
+template <int D, int NORM>
+static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const float* e_in, const float* e_out,
+                          const float* Wn, const float* B3, const float* gamma_e, const float* beta_e,
+                          const float* gamma_h, const float* beta_h, const float* P, const float* t,
+                          const float* z, const float* agg, const double* stats, const float* g_h,
+                          const float* g_e, float* g_h_in, float* g_e_in, float* dWn, float* dbn, float* dB3,
+                          float* db3, float* dgamma_e, float* dbeta_e, float* dgamma_h, float* dbeta_h,
+                          float* gP, float* G, float* g_eo, float* g_t, double* bstats, cudaStream_t st) {
+  const int64_t N = pl->N, E = pl->E;
+  GG_CUDA(cudaMemsetAsync(bstats, 0, sizeof(double) * 4 * D, st));
+  const unsigned grid = node_grid(N);
+  node_bwd_reduce_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, gamma_h, beta_h, bstats);
+  GG_LAUNCH_CHECK("node_bwd_reduce_kernel");
+  node_bwd_apply_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, bstats, gamma_h, beta_h,
+                                                               agg, gP, G);
+  GG_LAUNCH_CHECK("node_bwd_apply_kernel");
+  edge_bwd_a_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
+                                                           gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D);
+  GG_LAUNCH_CHECK("edge_bwd_a_kernel");
+  edge_bwd_b_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
+                                                           gamma_e, beta_e, g_t, gP);
+  GG_LAUNCH_CHECK("edge_bwd_b_kernel");
+  edge_bwd_src_kernel<D><<<grid, kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP);
+  GG_LAUNCH_CHECK("edge_bwd_src_kernel");
+  // g_e_in = g_eo (residual) + g_t B3 ; dB3 = g_t^T e_in ; db3 = colsum g_t
+  int rc = linear_bwd_data(E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
+  if (rc) return rc;
+  rc = linear_bwd_weight(E, D, D, g_t, D, e_in, D, dB3, db3, st);
+  if (rc) return rc;
+  // g_h_in = g_h (residual) + gP Wn ; dWn = gP^T h_in ; dbn = colsum gP
+  rc = linear_bwd_data(N, 5 * D, D, gP, 5 * D, Wn, D, residual ? g_h : nullptr, nullptr, g_h_in, D, st);
+  if (rc) return rc;
+  rc = linear_bwd_weight(N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, st);
+  if (rc) return rc;
+  affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats, dgamma_h, dbeta_h);
+  affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats + 2 * D, dgamma_e, dbeta_e);
+  GG_LAUNCH_CHECK("affine_grads_kernel");
+  return GG_OK;
+}
+
+// ------------------------------------------------------------------ predictor backward helpers
+// g_pre = g_score * w2 * [hid > 0] (in place over hid); red = [dw2 (H) | db1 (H) | db2 (1)] in fp64
+__global__ void __launch_bounds__(kNodeThreads)
+score_bwd_pre_kernel(int64_t E, const float* __restrict__ g_score, const float* __restrict__ w2,
+                     const float* hid, float* g_pre, double* __restrict__ red) {
+  constexpr int H = 64, VPL = 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * kNodeThreads) >> 5;
+  Row<H> w;
+  w.load(w2, lane);
+  double s1[VPL] = {0.0, 0.0}, s2[VPL] = {0.0, 0.0}, sg = 0.0;
+  for (int64_t i = gw; i < E; i += nw) {
+    const float gs = __ldg(g_score + i);
+    Row<H> h;
+    h.load_stream(hid + i * H, lane);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      s1[k] += (double)gs * (double)h.v[k];
+      const float gp = h.v[k] > 0.f ? gs * w.v[k] : 0.f;
+      s2[k] += (double)gp;
+      h.v[k] = gp;
+    }
+    h.store(g_pre + i * H, lane);
+    sg += (double)gs;
+  }
+  block_flush_stats<H>(s1, s2, red, red + H);
+  __shared__ double shg[kNodeThreads / 32];
+  if (lane == 0) shg[warp] = sg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int wi = 0; wi < kNodeThreads / 32; ++wi) a += shg[wi];
+    atomicAdd(red + 2 * H, a);
+  }
+}
+
+__global__ void score_small_grads_kernel(int H, const double* __restrict__ red, float* __restrict__ dw2,
+                                         float* __restrict__ dbq, float* __restrict__ db2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < H) {
+    dw2[c] = (float)red[c];
+    dbq[c] = (float)red[H + c];
+    dbq[H + c] = 0.f;
+  }
+  if (c == 0) db2[0] = (float)red[2 * H];
+}
+
+__global__ void gather_rows_kernel(int64_t rows, int width, const float* __restrict__ in,
+                                   const int32_t* __restrict__ idx, float* __restrict__ out) {
+  const int64_t total = rows * width;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = k / width;
+    const int c = (int)(k - r * width);
+    out[k] = __ldg(in + (int64_t)__ldg(idx + r) * width + c);
+  }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+#define GG_DISPATCH(d, norm, CALL)                                                  \
+  do {                                                                              \
+    if (norm == GG_NORM_BATCH) {                                                    \
+      if (d == 64) return CALL(64, GG_NORM_BATCH);                                  \
+      if (d == 128) return CALL(128, GG_NORM_BATCH);                                \
+      if (d == 256) return CALL(256, GG_NORM_BATCH);                                \
+    } else if (norm == GG_NORM_LAYER) {                                             \
+      if (d == 64) return CALL(64, GG_NORM_LAYER);                                  \
+      if (d == 128) return CALL(128, GG_NORM_LAYER);                                \
+      if (d == 256) return CALL(256, GG_NORM_LAYER);                                \
+    }                                                                               \
+    set_error("gnnome_b200: unsupported hidden size / norm kind (d in {64,128,256})"); \
+    return GG_ERR_UNSUPPORTED;                                                      \
+  } while (0)
+
+extern "C" {
+
+int gg_linear_fwd(int64_t M, int N, int K, const float* X, const float* W, const float* b, int relu, float* Y,
+                  void* stream) {
+  GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad sizes");
+  GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_fwd: N and K must be multiples of 4");
+  GG_REQUIRE(X && W && Y, "linear_fwd: null pointer");
+  return linear_fwd(M, N, K, X, K, W, K, b, relu, Y, N, (cudaStream_t)stream);
+}
+
+int gg_linear_bwd_data(int64_t M, int N, int K, const float* dY, const float* W, const float* addend,
+                       const float* relu_mask, float* dX, void* stream) {
+  GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_data: bad sizes");
+  GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_bwd_data: N and K must be multiples of 4");
+  GG_REQUIRE(dY && W && dX, "linear_bwd_data: null pointer");
+  return linear_bwd_data(M, N, K, dY, N, W, K, addend, relu_mask, dX, K, (cudaStream_t)stream);
+}
+
+int gg_linear_bwd_weight(int64_t M, int N, int K, const float* dY, const float* X, float* dW, float* db,
+                         void* stream) {
+  GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad sizes");
+  GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_bwd_weight: N and K must be multiples of 4");
+  GG_REQUIRE(dY && X && dW, "linear_bwd_weight: null pointer");
+  return linear_bwd_weight(M, N, K, dY, N, X, K, dW, db, (cudaStream_t)stream);
+}
+
+int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in, const float* e_in,
+                 const float* Wn, const float* bn, const float* B3, const float* b3, const float* gamma_e,
+                 const float* beta_e, const float* gamma_h, const float* beta_h, float* h_out, float* e_out,
+                 float* P, float* t, float* z, float* agg, double* stats, void* stream) {
+  GG_REQUIRE(plan, "layer_fwd: null plan");
+  GG_REQUIRE(h_in && e_in && Wn && bn && B3 && b3 && gamma_e && beta_e && gamma_h && beta_h,
+             "layer_fwd: null input");
+  GG_REQUIRE(h_out && e_out && P && t && z && agg && stats, "layer_fwd: null output/workspace");
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+#define CALL_FWD(DD, NN)                                                                                  \
+  layer_fwd_impl<DD, NN>(pl, residual, h_in, e_in, Wn, bn, B3, b3, gamma_e, beta_e, gamma_h, beta_h, h_out, \
+                         e_out, P, t, z, agg, stats, (cudaStream_t)stream)
+  GG_DISPATCH(d, norm_kind, CALL_FWD);
+#undef CALL_FWD
+}
+
+int gg_layer_bwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in, const float* e_in,
+                 const float* e_out, const float* Wn, const float* B3, const float* gamma_e, const float* beta_e,
+                 const float* gamma_h, const float* beta_h, const float* P, const float* t, const float* z,
+                 const float* agg, const double* stats, const float* g_h, const float* g_e, float* g_h_in,
+                 float* g_e_in, float* dWn, float* dbn, float* dB3, float* db3, float* dgamma_e, float* dbeta_e,
+                 float* dgamma_h, float* dbeta_h, float* gP, float* G, float* g_eo, float* g_t, double* bstats,
+                 void* stream) {
+  GG_REQUIRE(plan, "layer_bwd: null plan");
+  GG_REQUIRE(h_in && e_in && e_out && Wn && B3 && gamma_e && beta_e && gamma_h && beta_h && P && t && z && agg &&
+                 stats, "layer_bwd: null saved tensor");
+  GG_REQUIRE(g_h, "layer_bwd: g_h must be given (pass zeros when only e_out has a gradient)");
+  GG_REQUIRE(g_h_in && g_e_in && dWn && dbn && dB3 && db3 && dgamma_e && dbeta_e && dgamma_h && dbeta_h,
+             "layer_bwd: null output");
+  GG_REQUIRE(gP && G && g_eo && g_t && bstats, "layer_bwd: null workspace");
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+#define CALL_BWD(DD, NN)                                                                                      \
+  layer_bwd_impl<DD, NN>(pl, residual, h_in, e_in, e_out, Wn, B3, gamma_e, beta_e, gamma_h, beta_h, P, t, z, agg, \
+                         stats, g_h, g_e, g_h_in, g_e_in, dWn, dbn, dB3, db3, dgamma_e, dbeta_e, dgamma_h,   \
+                         dbeta_h, gP, G, g_eo, g_t, bstats, (cudaStream_t)stream)
+  GG_DISPATCH(d, norm_kind, CALL_BWD);
+#undef CALL_BWD
+}
+
+int gg_score_fwd(const gg_plan_t* plan, int d, int H, const float* x, const float* e, const float* Wq,
+                 const float* bq, const float* W1e, const float* w2, const float* b2, float* score, float* Q,
+                 float* hid, void* stream) {
+  GG_REQUIRE(plan, "score_fwd: null plan");
+  GG_REQUIRE(x && e && Wq && bq && W1e && w2 && b2 && score && Q, "score_fwd: null pointer");
+  if (H != 64 || !(d == 64 || d == 128 || d == 256)) {
+    set_error("gnnome_b200: score predictor supports H = 64 and d in {64,128,256}");
+    return GG_ERR_UNSUPPORTED;
+  }
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = linear_fwd(pl->N, 2 * H, d, x, d, Wq, d, bq, 0, Q, 2 * H, st);
+  if (rc) return rc;
+  if (pl->E == 0) return GG_OK;
+  GemmArgs g{};
+  g.A = e; g.lda = d; g.B = W1e; g.ldb = d; g.M = pl->E; g.N = H; g.K = d;
+  EpiScore epi{score, hid, Q, w2, b2, pl->src, pl->dst, pl->E};
+  return launch_gemm<64, false, true, false, false>(g, epi, 1, st);
+}
+
+int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const float* e, const float* Wq,
+                 const float* W1e, const float* w2, const float* g_score, const float* hid, float* g_x,
+                 float* g_e, float* dWq, float* dbq, float* dW1e, float* dw2, float* db2, float* g_pre,
+                 float* gQ, double* red, void* stream) {
+  GG_REQUIRE(plan, "score_bwd: null plan");
+  GG_REQUIRE(x && e && Wq && W1e && w2 && g_score && hid && g_x && g_e && dWq && dbq && dW1e && dw2 && db2 && g_pre && gQ &&
+                 red, "score_bwd: null pointer");
+  if (H != 64 || !(d == 64 || d == 128 || d == 256)) {
+    set_error("gnnome_b200: score predictor supports H = 64 and d in {64,128,256}");
+    return GG_ERR_UNSUPPORTED;
+  }
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = pl->N, E = pl->E;
+  GG_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * (2 * H + 1), st));
+  {
+    int64_t blocks = (E + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    score_bwd_pre_kernel<<<(unsigned)blocks, kNodeThreads, 0, st>>>(E, g_score, w2, hid, g_pre, red);
+    GG_LAUNCH_CHECK("score_bwd_pre_kernel");
+  }
+  score_small_grads_kernel<<<1, 64, 0, st>>>(H, red, dw2, dbq, db2);
+  GG_LAUNCH_CHECK("score_small_grads_kernel");
+  int rc = linear_bwd_data(E, H, d, g_pre, H, W1e, d, nullptr, nullptr, g_e, d, st);     // g_e = g_pre W1e
+  if (rc) return rc;
+  rc = linear_bwd_weight(E, H, d, g_pre, H, e, d, dW1e, nullptr, st);                      // dW1e = g_pre^T e
+  if (rc) return rc;
+  edge_to_node_sums_kernel<64><<<node_grid(N), kNodeThreads, 0, st>>>(N, pl->in_ptr, pl->out_ptr, pl->out_eid, g_pre, gQ);
+  GG_LAUNCH_CHECK("edge_to_node_sums_kernel");
+  rc = linear_bwd_data(N, 2 * H, d, gQ, 2 * H, Wq, d, nullptr, nullptr, g_x, d, st);    // g_x = gQ Wq
+  if (rc) return rc;
+  return linear_bwd_weight(N, 2 * H, d, gQ, 2 * H, x, d, dWq, nullptr, st);              // dWq = gQ^T x
+}
+
+int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx, float* out, void* stream) {
+  GG_REQUIRE(rows >= 0 && width > 0, "gather_rows: bad sizes");
+  if (rows == 0) return GG_OK;
+  GG_REQUIRE(in && idx && out, "gather_rows: null pointer");
+  int64_t blocks = (rows * width + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, width, in, idx, out);
+  GG_LAUNCH_CHECK("gather_rows_kernel");
+  return GG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// gg_common.cuh — shared device/host helpers for the GatedGCN engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/gnnome_b200.h"
+
+namespace gg {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GG_CUDA(call)                                              \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    if (_e != cudaSuccess) return gg::cuda_fail(_e, #call);        \
+  } while (0)
+
+#define GG_LAUNCH_CHECK(name)                                      \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return gg::cuda_fail(_e, name);         \
+  } while (0)
+
+#define GG_REQUIRE(cond, msg)                                      \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      gg::set_error(std::string("gnnome_b200: ") + msg);           \
+      return GG_ERR_ARG;                                           \
+    }                                                              \
+  } while (0)
+
+struct Plan {
+  int64_t N = 0, E = 0;
+  int32_t* src = nullptr;      // [E] internal (dst-sorted) order
+  int32_t* dst = nullptr;      // [E]
+  int32_t* in_ptr = nullptr;   // [N+1] CSR over in-edges: internal ids [in_ptr[v], in_ptr[v+1])
+  int32_t* out_ptr = nullptr;  // [N+1] CSR over out-edges
+  int32_t* out_eid = nullptr;  // [E] internal edge id of the j-th out-edge slot
+  int32_t* out_dst = nullptr;  // [E] dst of that edge (saves one indirection)
+  int32_t* perm = nullptr;     // [E] internal position -> caller edge id
+  int32_t* inv_perm = nullptr; // [E]
+  int num_sms = 148;
+};
+
+constexpr float kAggEps = 1e-6f;   // gated_gcn_full.py:130,143
+constexpr float kNormEps = 1e-5f;  // nn.BatchNorm1d / nn.LayerNorm default eps
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+// A feature row of D floats spread over one warp: VPL = D/32 values per lane.
+//   D = 64 : lane holds channels {2*lane, 2*lane+1}                       (one 64-bit access)
+//   D >= 128: lane holds channels {128*j + 4*lane .. +3}, j < D/128       (128-bit accesses)
+// Every warp-wide access touches whole 128-byte lines.
+template <int D>
+struct Row {
+  static constexpr int VPL = D / 32;
+  float v[VPL];
+
+  __device__ __forceinline__ void load(const float* __restrict__ row, int lane) {
+    if constexpr (D == 64) {
+      float2 t = __ldg(reinterpret_cast<const float2*>(row) + lane);
+      v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < D / 128; ++j) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(row + 128 * j) + lane);
+        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+    }
+  }
+  // streaming variant for E x d tensors that are touched once per kernel (do not pollute L1)
+  __device__ __forceinline__ void load_stream(const float* __restrict__ row, int lane) {
+    if constexpr (D == 64) {
+      float2 t = __ldcs(reinterpret_cast<const float2*>(row) + lane);
+      v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < D / 128; ++j) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(row + 128 * j) + lane);
+        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float* __restrict__ row, int lane) const {
+    if constexpr (D == 64) {
+      reinterpret_cast<float2*>(row)[lane] = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < D / 128; ++j)
+        reinterpret_cast<float4*>(row + 128 * j)[lane] =
+            make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  __device__ __forceinline__ void fill(float x) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) v[k] = x;
+  }
+  // channel index of element k held by `lane`
+  __device__ __forceinline__ static int channel(int k, int lane) {
+    if constexpr (D == 64) return 2 * lane + k;
+    else return 128 * (k >> 2) + 4 * lane + (k & 3);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+#endif  // __CUDACC__
+}  // namespace gg

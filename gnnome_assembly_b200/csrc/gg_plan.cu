@@ -1,0 +1,157 @@
+// gg_plan.cu — graph plan: internal edge order (CSR over in-edges), out-edge CSR, permutations.
+// Replaces the structural role of the DGLGraph argument and of dgl.reverse
+// (models/full_graph.py:22, layers/gated_gcn_full.py:115): dgl.reverse keeps edge ids and swaps
+// src/dst, which here is simply "walk the out-edge CSR instead of the in-edge CSR".
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "gg_common.cuh"
+
+namespace gg {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("gnnome_b200: CUDA error in ") + what + ": " + cudaGetErrorString(e);
+  return GG_ERR_CUDA;
+}
+
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+static void free_plan(Plan* p) {
+  if (!p) return;
+  cudaFree(p->src); cudaFree(p->dst); cudaFree(p->in_ptr); cudaFree(p->out_ptr);
+  cudaFree(p->out_eid); cudaFree(p->out_dst); cudaFree(p->perm); cudaFree(p->inv_perm);
+  delete p;
+}
+
+}  // namespace gg
+
+using gg::Plan;
+
+extern "C" {
+
+int gg_version(void) { return 100; }
+
+const char* gg_last_error(void) { return gg::last_error_cstr(); }
+
+int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t N, int64_t E, void* stream_, gg_plan_t** out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GG_REQUIRE(out != nullptr, "plan_create: out is null");
+  *out = nullptr;
+  GG_REQUIRE(N >= 0 && E >= 0, "plan_create: negative size");
+  GG_REQUIRE(N < (1LL << 31) && E < (1LL << 31), "plan_create: int32 indices only");
+  GG_REQUIRE(E == 0 || (src && dst), "plan_create: null edge list");
+  std::vector<int32_t> hs((size_t)E), hd((size_t)E);
+  if (E > 0) {
+    if (gg::is_device_ptr(src)) {
+      GG_CUDA(cudaMemcpyAsync(hs.data(), src, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      GG_CUDA(cudaMemcpyAsync(hd.data(), dst, E * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      GG_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      std::memcpy(hs.data(), src, E * sizeof(int32_t));
+      std::memcpy(hd.data(), dst, E * sizeof(int32_t));
+    }
+  }
+  for (int64_t i = 0; i < E; ++i)
+    GG_REQUIRE(hs[i] >= 0 && hs[i] < N && hd[i] >= 0 && hd[i] < N, "plan_create: node index out of range");
+
+  // stable counting sort by dst -> internal order
+  std::vector<int32_t> in_ptr((size_t)N + 1, 0), out_ptr((size_t)N + 1, 0);
+  for (int64_t i = 0; i < E; ++i) { in_ptr[hd[i] + 1]++; out_ptr[hs[i] + 1]++; }
+  for (int64_t v = 0; v < N; ++v) { in_ptr[v + 1] += in_ptr[v]; out_ptr[v + 1] += out_ptr[v]; }
+  std::vector<int32_t> perm((size_t)E), inv((size_t)E), isrc((size_t)E), idst((size_t)E);
+  {
+    std::vector<int32_t> cur(in_ptr.begin(), in_ptr.end() - 1);
+    for (int64_t i = 0; i < E; ++i) {
+      const int32_t p = cur[hd[i]]++;
+      perm[p] = (int32_t)i;
+      inv[i] = p;
+    }
+  }
+  for (int64_t p = 0; p < E; ++p) { isrc[p] = hs[perm[p]]; idst[p] = hd[perm[p]]; }
+  // out-edge CSR over internal ids (stable: increasing internal id within a source)
+  std::vector<int32_t> out_eid((size_t)E), out_dst((size_t)E);
+  {
+    std::vector<int32_t> cur(out_ptr.begin(), out_ptr.end() - 1);
+    for (int64_t p = 0; p < E; ++p) {
+      const int32_t slot = cur[isrc[p]]++;
+      out_eid[slot] = (int32_t)p;
+      out_dst[slot] = idst[p];
+    }
+  }
+
+  Plan* pl = new Plan();
+  pl->N = N; pl->E = E;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  auto up = [&](int32_t** d, const std::vector<int32_t>& h) -> cudaError_t {
+    const size_t bytes = (h.size() ? h.size() : 1) * sizeof(int32_t);
+    cudaError_t e = cudaMalloc((void**)d, bytes);
+    if (e != cudaSuccess) return e;
+    if (h.size()) e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = up(&pl->src, isrc);
+  if (e == cudaSuccess) e = up(&pl->dst, idst);
+  if (e == cudaSuccess) e = up(&pl->in_ptr, in_ptr);
+  if (e == cudaSuccess) e = up(&pl->out_ptr, out_ptr);
+  if (e == cudaSuccess) e = up(&pl->out_eid, out_eid);
+  if (e == cudaSuccess) e = up(&pl->out_dst, out_dst);
+  if (e == cudaSuccess) e = up(&pl->perm, perm);
+  if (e == cudaSuccess) e = up(&pl->inv_perm, inv);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // host staging vectors die at return
+  if (e != cudaSuccess) {
+    gg::free_plan(pl);
+    return gg::cuda_fail(e, "plan_create upload");
+  }
+  *out = reinterpret_cast<gg_plan_t*>(pl);
+  return GG_OK;
+}
+
+int gg_plan_destroy(gg_plan_t* plan) {
+  gg::free_plan(reinterpret_cast<Plan*>(plan));
+  return GG_OK;
+}
+
+#define GG_PLAN_GET(name, field, type, dflt)                              \
+  type name(const gg_plan_t* plan) {                                      \
+    return plan ? reinterpret_cast<const Plan*>(plan)->field : dflt;      \
+  }
+GG_PLAN_GET(gg_plan_num_nodes, N, int64_t, -1)
+GG_PLAN_GET(gg_plan_num_edges, E, int64_t, -1)
+GG_PLAN_GET(gg_plan_perm, perm, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_inv_perm, inv_perm, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_src, src, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_dst, dst, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_in_ptr, in_ptr, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_out_ptr, out_ptr, const int32_t*, nullptr)
+GG_PLAN_GET(gg_plan_out_eid, out_eid, const int32_t*, nullptr)
+
+
+int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream) {
+  GG_REQUIRE(plan && out, "plan_copy_array: null pointer");
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  const int32_t* srcs[7] = {p->perm, p->inv_perm, p->src, p->dst, p->in_ptr, p->out_ptr, p->out_eid};
+  GG_REQUIRE(which >= 0 && which < 7, "plan_copy_array: bad selector");
+  const int64_t n = (which == 4 || which == 5) ? p->N + 1 : p->E;
+  if (n > 0)
+    GG_CUDA(cudaMemcpyAsync(out, srcs[which], n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GG_OK;
+}
+
+}  // extern "C"

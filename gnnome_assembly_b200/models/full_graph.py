@@ -1,0 +1,33 @@
+"""GraphGatedGCNModel — drop-in for models/full_graph.py:11-29.
+
+Same positional constructor arguments, same state_dict keys (the shipped checkpoints load with
+strict=True), same `forward(graph, x, e, pe) -> scores [E, 1]` in the caller's edge-id order.  This is
+the primary seam of the engine: inside, everything runs in the plan's internal (dst-sorted) edge order;
+only the E x 2 input and the E x 1 output are permuted.
+"""
+import torch.nn as nn
+
+from .. import functional as GF
+from .. import layers
+from ..plan import plan_for
+
+
+class GraphGatedGCNModel(nn.Module):
+    def __init__(self, node_features, edge_features, hidden_features, hidden_edge_features, num_layers,
+                 hidden_edge_scores, batch_norm, nb_pos_enc):
+        super().__init__()
+        self.linear_pe = nn.Linear(nb_pos_enc + 2, hidden_features)
+        self.linear1_edge = nn.Linear(edge_features, hidden_edge_features)
+        self.linear2_edge = nn.Linear(hidden_edge_features, hidden_features)
+        self.gnn = layers.GraphGatedGCN(num_layers, hidden_features, batch_norm)
+        self.predictor = layers.ScorePredictor(hidden_features, hidden_edge_scores)
+
+    def forward(self, graph, x, e, pe):
+        plan = plan_for(graph, pe.device)
+        e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)                       # E x 2, edge-id -> internal
+        h = GF.linear(pe, self.linear_pe.weight, self.linear_pe.bias)              # full_graph.py:23 (x ignored)
+        e_int = GF.edge_mlp(e_int, self.linear1_edge.weight, self.linear1_edge.bias,
+                            self.linear2_edge.weight, self.linear2_edge.bias)      # :24-26
+        h, e_int = self.gnn.forward_internal(plan, h, e_int)                       # :27
+        s = self.predictor.forward_internal(plan, h, e_int)                        # :28
+        return GF.permute_rows(s.unsqueeze(-1), plan.inv_perm, plan.perm)          # internal -> edge-id, [E,1]

@@ -1,0 +1,124 @@
+/* gnnome_b200.h — C ABI of the B200-native GatedGCN message-passing engine.
+ *
+ * The reference (lvrcek/GNNome-assembly) has no FFI: its hot path is Python calling PyTorch and DGL.
+ * This header IS the new seam.  Each entry point names the reference interface it replaces
+ * (file:line relative to the reference repo).  All pointers are raw DEVICE pointers to fp32
+ * row-major contiguous arrays unless stated otherwise; `stream` is a cudaStream_t passed as void*.
+ * The caller owns every buffer (inputs, outputs, saved activations, workspace); the library owns
+ * only gg_plan_t.  No hidden allocation, no hidden stream, no device synchronisation inside the
+ * compute calls.  Return value: 0 = ok, <0 = error (see GG_ERR_*), message via gg_last_error().
+ *
+ * Supported sizes: hidden d in {64,128,256}; predictor hidden H = 64; indices int32.
+ */
+#ifndef GNNOME_B200_H
+#define GNNOME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_OK 0
+#define GG_ERR_ARG (-1)         /* null pointer, bad size, index out of range */
+#define GG_ERR_UNSUPPORTED (-2) /* hidden size / option the kernels are not built for */
+#define GG_ERR_CUDA (-3)        /* a CUDA runtime call failed; gg_last_error() has the string */
+
+#define GG_NORM_BATCH 0 /* nn.BatchNorm1d(track_running_stats=False), gated_gcn_full.py:55-56 */
+#define GG_NORM_LAYER 1 /* nn.LayerNorm, gated_gcn_full.py:58-59 */
+
+typedef struct gg_plan gg_plan_t;
+
+int gg_version(void);
+const char* gg_last_error(void);
+
+/* ---- graph plan -------------------------------------------------------------------------
+ * Replaces the structure side of the DGLGraph argument of GraphGatedGCNModel.forward
+ * (models/full_graph.py:22) and dgl.reverse (layers/gated_gcn_full.py:115).
+ * src/dst: int32[E] in the caller's edge-id order, HOST or DEVICE memory.  Builds, on the device,
+ * the internal edge order (stable sort by dst = CSR over in-edges) and a CSR over out-edges that
+ * points into it.  Internal position p holds caller edge perm[p]. */
+int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
+                   void* stream, gg_plan_t** out);
+int gg_plan_destroy(gg_plan_t* plan);
+int64_t gg_plan_num_nodes(const gg_plan_t* plan);
+int64_t gg_plan_num_edges(const gg_plan_t* plan);
+/* device int32[E]: perm (internal position -> caller edge id) and its inverse */
+const int32_t* gg_plan_perm(const gg_plan_t* plan);
+const int32_t* gg_plan_inv_perm(const gg_plan_t* plan);
+/* device int32 arrays in internal order: src[E], dst[E], in_ptr[N+1], out_ptr[N+1], out_eid[E] */
+const int32_t* gg_plan_src(const gg_plan_t* plan);
+const int32_t* gg_plan_dst(const gg_plan_t* plan);
+const int32_t* gg_plan_in_ptr(const gg_plan_t* plan);
+const int32_t* gg_plan_out_ptr(const gg_plan_t* plan);
+const int32_t* gg_plan_out_eid(const gg_plan_t* plan);
+/* copy one of those arrays into a caller-owned device buffer (async on `stream`);
+ * which: 0 perm, 1 inv_perm, 2 src, 3 dst, 4 in_ptr, 5 out_ptr, 6 out_eid */
+int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream);
+
+/* ---- dense linear ( nn.Linear ) -----------------------------------------------------------
+ * Replaces torch.nn.functional.linear at models/full_graph.py:23-26 (linear_pe, linear1_edge,
+ * linear2_edge).  Y[M,N] = X[M,K] * W[N,K]^T + b (b may be NULL); relu!=0 applies max(.,0).
+ * K and all leading dimensions must be multiples of 4 (callers zero-pad K = 18 -> 20, 2 -> 4). */
+int gg_linear_fwd(int64_t M, int N, int K, const float* X, const float* W, const float* b, int relu,
+                  float* Y, void* stream);
+/* dX[M,K] = dY[M,N] * W[N,K]  (+ addend[M,K] if not NULL); if relu_mask != NULL, dX is zeroed where
+ * relu_mask[M,K] <= 0 (relu_mask is the post-ReLU activation that produced X) */
+int gg_linear_bwd_data(int64_t M, int N, int K, const float* dY, const float* W, const float* addend,
+                       const float* relu_mask, float* dX, void* stream);
+/* dW[N,K] = dY[M,N]^T * X[M,K];  db[N] = column sums of dY (db may be NULL).
+ * dW and db are overwritten (zeroed inside, then accumulated split-K with fp32 atomics). */
+int gg_linear_bwd_weight(int64_t M, int N, int K, const float* dY, const float* X, float* dW, float* db,
+                         void* stream);
+
+/* ---- one GatedGCN layer ---------------------------------------------------------------------
+ * Replaces GatedGCN_1d.forward, layers/gated_gcn_full.py:99-157 (K1-K13 of SURVEY.md §2b).
+ * h_in[N,d], e_in[E,d] (e in INTERNAL edge order).  Wn[5d,d] = rows of A_1,A_2,A_3,B_1,B_2 stacked,
+ * bn[5d] their biases; B3[d,d], b3[d]; gamma/beta of bn_e and bn_h.
+ * Outputs h_out[N,d], e_out[E,d].  Saved for backward / scratch (caller allocated):
+ *   P[N,5d] projections, t[E,d] pre-norm edge gate, z[N,d] pre-norm node update,
+ *   agg[4,N,d] = hf | hb | 1/(den_f+eps) | 1/(den_b+eps),
+ *   stats[4d] doubles: sum_t | sum_t^2 | sum_z | sum_z^2 per channel (batch-norm only). */
+int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in,
+                 const float* e_in, const float* Wn, const float* bn, const float* B3, const float* b3,
+                 const float* gamma_e, const float* beta_e, const float* gamma_h, const float* beta_h,
+                 float* h_out, float* e_out, float* P, float* t, float* z, float* agg, double* stats,
+                 void* stream);
+
+/* Backward of the layer (the reference has no code for it: torch.autograd replays K16 of SURVEY §2b).
+ * g_h[N,d], g_e[E,d]: gradients w.r.t. h_out / e_out (either may be NULL = zero).
+ * Outputs: g_h_in[N,d], g_e_in[E,d], dWn[5d,d], dbn[5d], dB3[d,d], db3[d], dgamma/dbeta (4 x [d]).
+ * Workspace: gP[N,5d], G[2,N,2d], g_eo[E,d], g_t[E,d], bstats[4d] doubles.  g_e_in may alias g_eo. */
+int gg_layer_bwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in,
+                 const float* e_in, const float* e_out, const float* Wn, const float* B3,
+                 const float* gamma_e, const float* beta_e, const float* gamma_h, const float* beta_h,
+                 const float* P, const float* t, const float* z, const float* agg, const double* stats,
+                 const float* g_h, const float* g_e, float* g_h_in, float* g_e_in, float* dWn, float* dbn,
+                 float* dB3, float* db3, float* dgamma_e, float* dbeta_e, float* dgamma_h, float* dbeta_h,
+                 float* gP, float* G, float* g_eo, float* g_t, double* bstats, void* stream);
+
+/* ---- edge score predictor -----------------------------------------------------------------
+ * Replaces ScorePredictor.forward, layers/score_predictor.py:12-25 (K15), without materialising
+ * the E x 3d concat: W1 = [W1s | W1d | W1e] (columns), Wq[2H,d] = [W1s ; W1d] stacked by rows,
+ * bq[2H] = [b1 ; 0], W1e[H,d], w2[H], b2[1].  x[N,d], e[E,d] internal order.
+ * Outputs score[E] (internal order); Q[N,2H] scratch; hid[E,H] saved post-ReLU hidden (NULL to skip). */
+int gg_score_fwd(const gg_plan_t* plan, int d, int H, const float* x, const float* e, const float* Wq,
+                 const float* bq, const float* W1e, const float* w2, const float* b2, float* score,
+                 float* Q, float* hid, void* stream);
+/* g_score[E].  Outputs g_x[N,d], g_e[E,d], dWq[2H,d], dbq[2H] (second half zero), dW1e[H,d], dw2[H],
+ * db2[1].  Workspace g_pre[E,H] (may alias hid), gQ[N,2H], red[2H+1] doubles. */
+int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const float* e, const float* Wq,
+                 const float* W1e, const float* w2, const float* g_score, const float* hid, float* g_x,
+                 float* g_e, float* dWq, float* dbq, float* dW1e, float* dw2, float* db2, float* g_pre,
+                 float* gQ, double* red, void* stream);
+
+/* ---- edge-order helpers ------------------------------------------------------------------------
+ * out[p, :] = in[idx[p], :]  (rows of `width` floats).  Used to move e[E,2] / scores[E] between the
+ * caller's edge-id order (the contract at the model boundary) and the internal order. */
+int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNOME_B200_H */
