@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — edges/s of the GatedGCN training step (fwd + bwd + Adam) on a chr19-like assembly graph.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N=1 = BASELINE.json configs[1]: 8-layer GatedGCN, d=128, BatchNorm, one chr19-like synthetic
+assembly graph (seed 0; N~45.9k nodes, E~372.7k edges), forward + BCEWithLogits loss + backward + Adam
+step, i.e. the loop body of train.py:245-258.  N>1 (torchrun): one independent chr19-like graph per rank
+(seed = rank), one NCCL all-reduce of the flat gradient per step (weak scaling).
+
+One JSON line on stdout (rank 0).  `value`: edges/s with inputs resident in HBM; `e2e`: the same step
+driven from pinned HOST buffers (H2D of e, pe, y and D2H of the loss inside the timed region);
+`roofline`: the dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json;
+`cpu_baseline`: the oracle (CPU restatement of the reference) on the host cores, bounded sample.
+`--impl reference` times that CPU oracle as the main line (DGL is not installable, so the reference's
+own forward cannot run; the oracle is pinned to the reference code by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, L, HID_E, HID_S, NB_PE = 128, 8, 16, 64, 16
+POS_WEIGHT = 1.0 / 16.5
+METRIC = "edges/s GatedGCN fwd+bwd on chr19 assembly graph"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mx = float(parts[1])
+                if t0 - 0.03 <= ts <= t1 + 0.03:
+                    sm.append(float(parts[0]))
+                    power.append(float(parts[2]))
+                    for nm, val in zip(names, parts[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def make_graph(seed, scale=1.0):
+    from gnnome_assembly_b200.synth import CHR_LEN, make_assembly_graph
+    return make_assembly_graph("chr19", seed=seed, genome_len=int(CHR_LEN["chr19"] * scale))
+
+
+def cpu_oracle_rate(steps, warmup, scale):
+    """edges/s of the oracle training step on the host cores (all threads torch can use)."""
+    from oracle.gatedgcn_oracle import OracleModel, bce_loss
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = make_graph(0, scale)
+    torch.manual_seed(0)
+    model = OracleModel(1, 2, D, HID_E, L, HID_S, True, NB_PE)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    src = torch.from_numpy(g.src.astype(np.int64))
+    dst = torch.from_numpy(g.dst.astype(np.int64))
+    e, pe, y = torch.from_numpy(g.e), torch.from_numpy(g.pe), torch.from_numpy(g.y)
+
+    def step():
+        loss = bce_loss(model(src, dst, g.num_nodes, e, pe), y, POS_WEIGHT)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sample = (f"chr19-like graph at {scale:g}x genome length (N={g.num_nodes}, E={g.num_edges}), L={L} d={D} "
+              f"fwd+bwd+Adam, {steps} timed steps after {warmup} warm-up")
+    return g.num_edges / dt, dt, torch.get_num_threads(), sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, dt, cores, sample = cpu_oracle_rate(args.steps, max(args.warmup, 1), scale=0.125)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 8-layer GatedGCN d=128 fwd+bwd(+Adam) on a chr19-like assembly graph",
+                   "layers": L, "hidden": D, "norm": "batch", "note": "CPU oracle (pure-PyTorch restatement of the "
+                   "reference forward; DGL not installable), bounded sample"},
+        "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ kernel table
+def algorithmic_bytes(E, N, d, H=64):
+    """Algorithmic bytes per launch for each kernel (fp32; node arrays counted once = perfect L2 reuse).
+    DESIGN.md §'Kernels' derives every entry."""
+    return {
+        "gemm_node_proj": 4 * d * N + 20 * d * N,                       # read h, write P[N,5d]
+        "gemm_edge_gate": 8 * d * E + 8 * d * N + 8 * E,                # read e_in, write t, B1h/B2h rows, src/dst
+        "edge_gate_fwd_kernel": 12 * d * E + 12 * d * N + 4 * E,        # read t,e_in; write e_out; A2h; hf,1/den
+        "node_agg_fwd_kernel": 4 * d * E + 28 * d * N + 8 * E,          # read e_out; A3h,A1h,hf; write hb,1/den,z
+        "node_update_fwd_kernel": 12 * d * N,
+        "node_bwd_reduce_kernel": 8 * d * N,
+        "node_bwd_apply_kernel": 8 * d * N + 16 * d * N + 4 * d * N + 16 * d * N,
+        "edge_bwd_a_kernel": 16 * d * E + 28 * d * N + 4 * E,           # read t,e_in,g_e; write g_eo; Gf,Gb,A2h,A3h; gA3h
+        "edge_bwd_b_kernel": 12 * d * E + 4 * d * N,                    # read t,g_eo; write g_t; gB2h
+        "edge_bwd_src_kernel": 8 * d * E + 12 * d * N + 8 * E,          # read g_t,e_out; gnf; write gB1h,gA2h
+        "gemm_bwd_e_in": 12 * d * E,                                    # read g_t,g_eo; write g_e_in
+        "gemm_dB3": 8 * d * E,                                          # read g_t,e_in
+        "gemm_bwd_h_in": 20 * d * N + 8 * d * N,
+        "gemm_dWn": 20 * d * N + 4 * d * N,
+        "gemm_score": 4 * d * E + 4 * H * E + 8 * H * N + 12 * E,       # read e; write hid; Q rows; idx, score
+        "gemm_score_q": 4 * d * N + 8 * H * N,
+        "score_bwd_pre_kernel": 8 * H * E + 4 * E,
+        "gemm_score_bwd_e": 4 * H * E + 4 * d * E,
+        "gemm_score_dW1e": 4 * H * E + 4 * d * E,
+        "edge_to_node_sums_kernel": 8 * H * E + 8 * H * N,
+        "gemm_score_bwd_x": 8 * H * N + 4 * d * N,
+        "gemm_score_dWq": 8 * H * N + 4 * d * N,
+    }
+
+
+def step_algorithmic_bytes(E, N, d, layers):
+    """fwd+bwd = 4d(11E + 67N) + 32E per layer (fused two-pass design, unique node rows)."""
+    return layers * (4 * d * (11 * E + 67 * N) + 32 * E)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200 import _lib
+    from gnnome_assembly_b200.dp import GradBucket
+    from oracle.gatedgcn_oracle import bce_loss          # loss = train.py:211; plain torch op on the logits
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device — the GatedGCN engine has no CPU path "
+                           "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    g = make_graph(seed=rank)
+    E, N = g.num_edges, g.num_nodes
+    torch.manual_seed(0)
+    model = gg.GraphGatedGCNModel(1, 2, D, HID_E, L, HID_S, True, NB_PE).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    bucket = GradBucket(model.parameters()) if world > 1 else None
+    graph = gg.AssemblyGraph(torch.from_numpy(g.src), torch.from_numpy(g.dst), N)
+    gg.plan_for(graph, dev)                                    # plan creation excluded from timing (once per graph)
+    # pinned host copies (the e2e arm) and device-resident copies (the kernel arm)
+    h_e, h_pe, h_y = (torch.from_numpy(a).pin_memory() for a in (g.e, g.pe, g.y))
+    d_e, d_pe, d_y = h_e.to(dev), h_pe.to(dev), h_y.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(e, pe, y):
+        scores = model(graph, None, e, pe)
+        loss = bce_loss(scores, y, POS_WEIGHT)
+        opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if bucket is not None:
+            bucket.allreduce_mean(active=True)
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, host_inputs):
+        evs = []
+        for _ in range(n_steps):
+            flush.zero_()                                      # L2 flush between steps, outside the event pair
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if host_inputs:
+                e = h_e.to(dev, non_blocking=True)
+                pe = h_pe.to(dev, non_blocking=True)
+                y = h_y.to(dev, non_blocking=True)
+                loss = step(e, pe, y)
+                loss.item()                                    # D2H of the step's result (train.py:259)
+            else:
+                step(d_e, d_pe, d_y)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / 1e3    # seconds
+
+    for _ in range(max(args.warmup, 3)):
+        step(d_e, d_pe, d_y)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = _lib.launch_count()
+    t_wall0 = time.perf_counter()
+    t_dev = timed(args.steps, host_inputs=False)
+    sync_all()
+    t_wall1 = time.perf_counter()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # e2e: same step from pinned host buffers, loss read back every step
+    timed(2, host_inputs=True)
+    sync_all()
+    t_e2e = timed(args.steps, host_inputs=True)
+    sync_all()
+
+    # per-kernel pass: CUDA event pair around every launch, on the launching stream (not the timed region)
+    prof = {}
+    if rank == 0:
+        _lib.profile(True)
+        for _ in range(3):
+            flush.zero_()
+            step(d_e, d_pe, d_y)
+        torch.cuda.synchronize()
+        _lib.profile(False)
+        prof = _lib.profile_report()
+
+    # max over ranks, sum of edges
+    t = torch.tensor([t_dev, t_e2e, float(E)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e, edges_total = float(tm[0]), float(tm[1]), float(t[2])
+    else:
+        edges_total = float(E)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    ms_step = t_dev / args.steps * 1e3
+    value = edges_total * args.steps / t_dev
+    e2e_val = edges_total * args.steps / t_e2e
+    ab = algorithmic_bytes(E, N, D)
+    total_ms = sum(v[1] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        avg_s = ms / cnt / 1e3
+        row = {"launches_per_step": cnt / 3, "avg_us": avg_s * 1e6, "share": ms / total_ms}
+        if name in ab:
+            row["gbps"] = ab[name] / avg_s / 1e9
+            row["frac"] = row["gbps"] / peak
+        kernels[name] = row
+    dom = next((k for k in kernels if k in ab), None)
+    roofline = None
+    if dom:
+        r = kernels[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": r["gbps"], "peak": peak, "unit": "GB/s",
+                    "frac": r["frac"], "traffic": None, "peak_source": peak_src, "share_of_step": r["share"],
+                    "timing": "CUDA event pair per launch on the launching stream, 3 extra steps after the timed region",
+                    "algorithmic_bytes_per_launch": ab[dom]}
+    step_bytes = step_algorithmic_bytes(E, N, D, L)
+    cpu_val, cpu_dt, cores, sample = cpu_oracle_rate(steps=3, warmup=1, scale=0.25) if world == 1 else (None,) * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 8-layer GatedGCN d=128 (BatchNorm) fwd+bwd+Adam on one chr19-like "
+                   "synthetic assembly graph per GPU", "layers": L, "hidden": D, "nodes": N, "edges": E,
+                   "parallelism": f"dp{world} (independent graphs, NCCL grad all-reduce)" if world > 1 else "single GPU",
+                   "l2": "512 MB memset between timed steps (outside the per-step event pairs); per-step working "
+                   "set ~5 GB >> 126 MB L2"},
+        "edge_layers_per_s": value * L,
+        "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": t_e2e / args.steps * 1e3,
+                "h2d_bytes_per_step": int(h_e.numel() * 4 + h_pe.numel() * 4 + h_y.numel() * 4) * world,
+                "d2h_bytes_per_step": 4 * world},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbps": step_bytes / (ms_step / 1e3) / 1e9,
+                          "frac": step_bytes / (ms_step / 1e3) / 1e9 / peak,
+                          "formula": "SURVEY 8d: L*(4d(11E+67N)+32E), the fused two-pass ideal"},
+        "kernels": kernels,
+        "clocks": clocks,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
+                                "ms_per_step": cpu_dt * 1e3}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

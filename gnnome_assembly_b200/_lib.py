@@ -19,6 +19,9 @@ _i64 = C.c_int64
 SIGNATURES = {
     "gg_version": (_i, []),
     "gg_last_error": (C.c_char_p, []),
+    "gg_launch_count": (_i64, []),
+    "gg_profile_enable": (_i, [_i]),
+    "gg_profile_report": (_i, [C.c_char_p, C.c_size_t]),
     "gg_plan_create": (_i, [_p, _p, _i64, _i64, _p, C.POINTER(_p)]),
     "gg_plan_destroy": (_i, [_p]),
     "gg_plan_num_nodes": (_i64, [_p]),
@@ -69,3 +72,19 @@ def check(rc, what):
 def ptr(t):
     """Device/host pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def launch_count():
+    return int(lib().gg_launch_count())
+
+
+def profile(on):
+    check(lib().gg_profile_enable(1 if on else 0), "gg_profile_enable")
+
+
+def profile_report():
+    """{kernel name: (launches, total_ms)} for the launches made while profiling was on."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().gg_profile_report(buf, len(buf)), "gg_profile_report")
+    return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}

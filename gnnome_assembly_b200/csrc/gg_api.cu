@@ -36,29 +36,29 @@ static int pick_splits(int64_t K, int64_t tiles) {
 
 // ------------------------------------------------------------------ generic GEMM front-ends
 // Y[M,N] = X[M,K] W[N,K]^T (+b)(relu)
-static int linear_fwd(int64_t M, int N, int K, const float* X, int64_t ldx, const float* W, int64_t ldw,
+static int linear_fwd(const char* tag, int64_t M, int N, int K, const float* X, int64_t ldx, const float* W, int64_t ldw,
                       const float* b, int relu, float* Y, int64_t ldy, cudaStream_t st) {
   GemmArgs g{};
   g.A = X; g.lda = ldx; g.B = W; g.ldb = ldw; g.M = M; g.N = N; g.K = K;
   EpiBias epi{Y, ldy, b, relu};
-  if (N >= 128) return launch_gemm<128, false, true, false, false>(g, epi, 1, st);
-  if (N > 32) return launch_gemm<64, false, true, false, false>(g, epi, 1, st);
-  return launch_gemm<32, false, true, false, false>(g, epi, 1, st);
+  if (N >= 128) return launch_gemm<128, false, true, false, false>(tag, g, epi, 1, st);
+  if (N > 32) return launch_gemm<64, false, true, false, false>(tag, g, epi, 1, st);
+  return launch_gemm<32, false, true, false, false>(tag, g, epi, 1, st);
 }
 
 // dX[M,K] = dY[M,N] W[N,K] (+addend)(mask)
-static int linear_bwd_data(int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
+static int linear_bwd_data(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
                            const float* addend, const float* mask, float* dX, int64_t lddx, cudaStream_t st) {
   GemmArgs g{};
   g.A = dY; g.lda = lddy; g.B = W; g.ldb = ldw; g.M = M; g.N = K; g.K = N;
   EpiAddMask epi{dX, lddx, addend, mask};
-  if (K >= 128) return launch_gemm<128, false, false, false, false>(g, epi, 1, st);
-  if (K > 32) return launch_gemm<64, false, false, false, false>(g, epi, 1, st);
-  return launch_gemm<32, false, false, false, false>(g, epi, 1, st);
+  if (K >= 128) return launch_gemm<128, false, false, false, false>(tag, g, epi, 1, st);
+  if (K > 32) return launch_gemm<64, false, false, false, false>(tag, g, epi, 1, st);
+  return launch_gemm<32, false, false, false, false>(tag, g, epi, 1, st);
 }
 
 // dW[N,K] = dY[M,N]^T X[M,K] ; db[N] = colsum(dY)       (dW, db zeroed here)
-static int linear_bwd_weight(int64_t M, int N, int K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
+static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
                              float* dW, float* db, cudaStream_t st) {
   GG_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
   if (db) GG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
@@ -68,9 +68,9 @@ static int linear_bwd_weight(int64_t M, int N, int K, const float* dY, int64_t l
   g.bias_grad = db;
   EpiAtomic epi{dW, (int64_t)K};
   const int64_t m_tiles = (N + kBM - 1) / kBM;
-  if (K >= 128) return launch_gemm<128, true, false, false, true>(g, epi, pick_splits(M, m_tiles * ((K + 127) / 128)), st);
-  if (K > 32) return launch_gemm<64, true, false, false, true>(g, epi, pick_splits(M, m_tiles), st);
-  return launch_gemm<32, true, false, false, true>(g, epi, pick_splits(M, m_tiles), st);
+  if (K >= 128) return launch_gemm<128, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles * ((K + 127) / 128)), st);
+  if (K > 32) return launch_gemm<64, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles), st);
+  return launch_gemm<32, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles), st);
 }
 
 // ------------------------------------------------------------------ layer forward / backward
@@ -82,7 +82,7 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
   const int64_t N = pl->N, E = pl->E;
   GG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * D, st));
   // node projections P = h [A1|A2|A3|B1|B2]^T + b      (gated_gcn_full.py:107-112)
-  int rc = linear_fwd(N, 5 * D, D, h_in, D, Wn, D, bn, 0, P, 5 * D, st);
+  int rc = linear_fwd("gemm_node_proj", N, 5 * D, D, h_in, D, Wn, D, bn, 0, P, 5 * D, st);
   if (rc) return rc;
   // t = B3 e + b3 + B1h[src] + B2h[dst], with batch statistics  (:113,120-121)
   {
@@ -91,18 +91,21 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     g.col_stats = stats;
     EpiEdgeGate epi{t, D, b3, P, pl->src, pl->dst};
     constexpr int BN = D >= 128 ? 128 : 64;
-    rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>(g, epi, 1, st);
+    rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
     if (rc) return rc;
   }
+  GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
   edge_gate_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
       N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
-  GG_LAUNCH_CHECK("edge_gate_fwd_kernel");
+  GG_KERNEL_END("edge_gate_fwd_kernel", st);
+  GG_KERNEL_BEGIN("node_agg_fwd_kernel", st);
   node_agg_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
       N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D);
-  GG_LAUNCH_CHECK("node_agg_fwd_kernel");
+  GG_KERNEL_END("node_agg_fwd_kernel", st);
+  GG_KERNEL_BEGIN("node_update_fwd_kernel", st);
   node_update_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
       N, z, h_in, stats + 2 * D, gamma_h, beta_h, residual, h_out);
-  GG_LAUNCH_CHECK("node_update_fwd_kernel");
+  GG_KERNEL_END("node_update_fwd_kernel", st);
   return GG_OK;
 }
 
@@ -117,32 +120,40 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   const int64_t N = pl->N, E = pl->E;
   GG_CUDA(cudaMemsetAsync(bstats, 0, sizeof(double) * 4 * D, st));
   const unsigned grid = node_grid(N);
+  GG_KERNEL_BEGIN("node_bwd_reduce_kernel", st);
   node_bwd_reduce_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, gamma_h, beta_h, bstats);
-  GG_LAUNCH_CHECK("node_bwd_reduce_kernel");
+  GG_KERNEL_END("node_bwd_reduce_kernel", st);
+  GG_KERNEL_BEGIN("node_bwd_apply_kernel", st);
   node_bwd_apply_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, bstats, gamma_h, beta_h,
                                                                agg, gP, G);
-  GG_LAUNCH_CHECK("node_bwd_apply_kernel");
+  GG_KERNEL_END("node_bwd_apply_kernel", st);
+  GG_KERNEL_BEGIN("edge_bwd_a_kernel", st);
   edge_bwd_a_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
                                                            gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D);
-  GG_LAUNCH_CHECK("edge_bwd_a_kernel");
+  GG_KERNEL_END("edge_bwd_a_kernel", st);
+  GG_KERNEL_BEGIN("edge_bwd_b_kernel", st);
   edge_bwd_b_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
                                                            gamma_e, beta_e, g_t, gP);
-  GG_LAUNCH_CHECK("edge_bwd_b_kernel");
+  GG_KERNEL_END("edge_bwd_b_kernel", st);
+  GG_KERNEL_BEGIN("edge_bwd_src_kernel", st);
   edge_bwd_src_kernel<D><<<grid, kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP);
-  GG_LAUNCH_CHECK("edge_bwd_src_kernel");
+  GG_KERNEL_END("edge_bwd_src_kernel", st);
   // g_e_in = g_eo (residual) + g_t B3 ; dB3 = g_t^T e_in ; db3 = colsum g_t
-  int rc = linear_bwd_data(E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
+  int rc = linear_bwd_data("gemm_bwd_e_in", E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
   if (rc) return rc;
-  rc = linear_bwd_weight(E, D, D, g_t, D, e_in, D, dB3, db3, st);
+  rc = linear_bwd_weight("gemm_dB3", E, D, D, g_t, D, e_in, D, dB3, db3, st);
   if (rc) return rc;
   // g_h_in = g_h (residual) + gP Wn ; dWn = gP^T h_in ; dbn = colsum gP
-  rc = linear_bwd_data(N, 5 * D, D, gP, 5 * D, Wn, D, residual ? g_h : nullptr, nullptr, g_h_in, D, st);
+  rc = linear_bwd_data("gemm_bwd_h_in", N, 5 * D, D, gP, 5 * D, Wn, D, residual ? g_h : nullptr, nullptr, g_h_in, D, st);
   if (rc) return rc;
-  rc = linear_bwd_weight(N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, st);
+  rc = linear_bwd_weight("gemm_dWn", N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, st);
   if (rc) return rc;
+  GG_KERNEL_BEGIN("affine_grads_kernel", st);
   affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats, dgamma_h, dbeta_h);
+  GG_KERNEL_END("affine_grads_kernel", st);
+  GG_KERNEL_BEGIN("affine_grads_kernel", st);
   affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats + 2 * D, dgamma_e, dbeta_e);
-  GG_LAUNCH_CHECK("affine_grads_kernel");
+  GG_KERNEL_END("affine_grads_kernel", st);
   return GG_OK;
 }
 
@@ -229,24 +240,26 @@ int gg_linear_fwd(int64_t M, int N, int K, const float* X, const float* W, const
                   void* stream) {
   GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad sizes");
   GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_fwd: N and K must be multiples of 4");
+  if (M == 0) return GG_OK;
   GG_REQUIRE(X && W && Y, "linear_fwd: null pointer");
-  return linear_fwd(M, N, K, X, K, W, K, b, relu, Y, N, (cudaStream_t)stream);
+  return linear_fwd("gemm_linear_fwd", M, N, K, X, K, W, K, b, relu, Y, N, (cudaStream_t)stream);
 }
 
 int gg_linear_bwd_data(int64_t M, int N, int K, const float* dY, const float* W, const float* addend,
                        const float* relu_mask, float* dX, void* stream) {
   GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_data: bad sizes");
   GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_bwd_data: N and K must be multiples of 4");
+  if (M == 0) return GG_OK;
   GG_REQUIRE(dY && W && dX, "linear_bwd_data: null pointer");
-  return linear_bwd_data(M, N, K, dY, N, W, K, addend, relu_mask, dX, K, (cudaStream_t)stream);
+  return linear_bwd_data("gemm_linear_bwd_data", M, N, K, dY, N, W, K, addend, relu_mask, dX, K, (cudaStream_t)stream);
 }
 
 int gg_linear_bwd_weight(int64_t M, int N, int K, const float* dY, const float* X, float* dW, float* db,
                          void* stream) {
   GG_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad sizes");
   GG_REQUIRE(N % 4 == 0 && K % 4 == 0, "linear_bwd_weight: N and K must be multiples of 4");
-  GG_REQUIRE(dY && X && dW, "linear_bwd_weight: null pointer");
-  return linear_bwd_weight(M, N, K, dY, N, X, K, dW, db, (cudaStream_t)stream);
+  GG_REQUIRE(dW && (M == 0 || (dY && X)), "linear_bwd_weight: null pointer");
+  return linear_bwd_weight("gemm_linear_bwd_weight", M, N, K, dY, N, X, K, dW, db, (cudaStream_t)stream);
 }
 
 int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in, const float* e_in,
@@ -254,10 +267,10 @@ int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, cons
                  const float* beta_e, const float* gamma_h, const float* beta_h, float* h_out, float* e_out,
                  float* P, float* t, float* z, float* agg, double* stats, void* stream) {
   GG_REQUIRE(plan, "layer_fwd: null plan");
-  GG_REQUIRE(h_in && e_in && Wn && bn && B3 && b3 && gamma_e && beta_e && gamma_h && beta_h,
-             "layer_fwd: null input");
-  GG_REQUIRE(h_out && e_out && P && t && z && agg && stats, "layer_fwd: null output/workspace");
   const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  GG_REQUIRE(Wn && bn && B3 && b3 && gamma_e && beta_e && gamma_h && beta_h && stats, "layer_fwd: null parameter");
+  GG_REQUIRE(pl->N == 0 || (h_in && h_out && P && z && agg), "layer_fwd: null node buffer");
+  GG_REQUIRE(pl->E == 0 || (e_in && e_out && t), "layer_fwd: null edge buffer");
 #define CALL_FWD(DD, NN)                                                                                  \
   layer_fwd_impl<DD, NN>(pl, residual, h_in, e_in, Wn, bn, B3, b3, gamma_e, beta_e, gamma_h, beta_h, h_out, \
                          e_out, P, t, z, agg, stats, (cudaStream_t)stream)
@@ -273,13 +286,12 @@ int gg_layer_bwd(const gg_plan_t* plan, int d, int norm_kind, int residual, cons
                  float* dgamma_h, float* dbeta_h, float* gP, float* G, float* g_eo, float* g_t, double* bstats,
                  void* stream) {
   GG_REQUIRE(plan, "layer_bwd: null plan");
-  GG_REQUIRE(h_in && e_in && e_out && Wn && B3 && gamma_e && beta_e && gamma_h && beta_h && P && t && z && agg &&
-                 stats, "layer_bwd: null saved tensor");
-  GG_REQUIRE(g_h, "layer_bwd: g_h must be given (pass zeros when only e_out has a gradient)");
-  GG_REQUIRE(g_h_in && g_e_in && dWn && dbn && dB3 && db3 && dgamma_e && dbeta_e && dgamma_h && dbeta_h,
-             "layer_bwd: null output");
-  GG_REQUIRE(gP && G && g_eo && g_t && bstats, "layer_bwd: null workspace");
   const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  GG_REQUIRE(Wn && B3 && gamma_e && beta_e && gamma_h && beta_h && stats && bstats, "layer_bwd: null parameter");
+  GG_REQUIRE(dWn && dbn && dB3 && db3 && dgamma_e && dbeta_e && dgamma_h && dbeta_h, "layer_bwd: null output");
+  GG_REQUIRE(pl->N == 0 || (h_in && P && z && agg && g_h_in && gP && G), "layer_bwd: null node buffer");
+  GG_REQUIRE(pl->N == 0 || g_h, "layer_bwd: g_h must be given (pass zeros when only e_out has a gradient)");
+  GG_REQUIRE(pl->E == 0 || (e_in && e_out && t && g_e_in && g_eo && g_t), "layer_bwd: null edge buffer");
 #define CALL_BWD(DD, NN)                                                                                      \
   layer_bwd_impl<DD, NN>(pl, residual, h_in, e_in, e_out, Wn, B3, gamma_e, beta_e, gamma_h, beta_h, P, t, z, agg, \
                          stats, g_h, g_e, g_h_in, g_e_in, dWn, dbn, dB3, db3, dgamma_e, dbeta_e, dgamma_h,   \
@@ -292,20 +304,22 @@ int gg_score_fwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
                  const float* bq, const float* W1e, const float* w2, const float* b2, float* score, float* Q,
                  float* hid, void* stream) {
   GG_REQUIRE(plan, "score_fwd: null plan");
-  GG_REQUIRE(x && e && Wq && bq && W1e && w2 && b2 && score && Q, "score_fwd: null pointer");
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  GG_REQUIRE(Wq && bq && W1e && w2 && b2, "score_fwd: null parameter");
+  GG_REQUIRE(pl->N == 0 || (x && Q), "score_fwd: null node buffer");
+  GG_REQUIRE(pl->E == 0 || (e && score), "score_fwd: null edge buffer");
   if (H != 64 || !(d == 64 || d == 128 || d == 256)) {
     set_error("gnnome_b200: score predictor supports H = 64 and d in {64,128,256}");
     return GG_ERR_UNSUPPORTED;
   }
-  const Plan* pl = reinterpret_cast<const Plan*>(plan);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = linear_fwd(pl->N, 2 * H, d, x, d, Wq, d, bq, 0, Q, 2 * H, st);
+  int rc = linear_fwd("gemm_score_q", pl->N, 2 * H, d, x, d, Wq, d, bq, 0, Q, 2 * H, st);
   if (rc) return rc;
   if (pl->E == 0) return GG_OK;
   GemmArgs g{};
   g.A = e; g.lda = d; g.B = W1e; g.ldb = d; g.M = pl->E; g.N = H; g.K = d;
   EpiScore epi{score, hid, Q, w2, b2, pl->src, pl->dst, pl->E};
-  return launch_gemm<64, false, true, false, false>(g, epi, 1, st);
+  return launch_gemm<64, false, true, false, false>("gemm_score", g, epi, 1, st);
 }
 
 int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const float* e, const float* Wq,
@@ -313,13 +327,14 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
                  float* g_e, float* dWq, float* dbq, float* dW1e, float* dw2, float* db2, float* g_pre,
                  float* gQ, double* red, void* stream) {
   GG_REQUIRE(plan, "score_bwd: null plan");
-  GG_REQUIRE(x && e && Wq && W1e && w2 && g_score && hid && g_x && g_e && dWq && dbq && dW1e && dw2 && db2 && g_pre && gQ &&
-                 red, "score_bwd: null pointer");
+  const Plan* pl = reinterpret_cast<const Plan*>(plan);
+  GG_REQUIRE(Wq && W1e && w2 && dWq && dbq && dW1e && dw2 && db2 && red, "score_bwd: null parameter / output");
+  GG_REQUIRE(pl->N == 0 || (x && g_x && gQ), "score_bwd: null node buffer");
+  GG_REQUIRE(pl->E == 0 || (e && g_score && hid && g_e && g_pre), "score_bwd: null edge buffer");
   if (H != 64 || !(d == 64 || d == 128 || d == 256)) {
     set_error("gnnome_b200: score predictor supports H = 64 and d in {64,128,256}");
     return GG_ERR_UNSUPPORTED;
   }
-  const Plan* pl = reinterpret_cast<const Plan*>(plan);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = pl->N, E = pl->E;
   GG_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * (2 * H + 1), st));
@@ -328,31 +343,36 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    GG_KERNEL_BEGIN("score_bwd_pre_kernel", st);
     score_bwd_pre_kernel<<<(unsigned)blocks, kNodeThreads, 0, st>>>(E, g_score, w2, hid, g_pre, red);
-    GG_LAUNCH_CHECK("score_bwd_pre_kernel");
+    GG_KERNEL_END("score_bwd_pre_kernel", st);
   }
+  GG_KERNEL_BEGIN("score_small_grads_kernel", st);
   score_small_grads_kernel<<<1, 64, 0, st>>>(H, red, dw2, dbq, db2);
-  GG_LAUNCH_CHECK("score_small_grads_kernel");
-  int rc = linear_bwd_data(E, H, d, g_pre, H, W1e, d, nullptr, nullptr, g_e, d, st);     // g_e = g_pre W1e
+  GG_KERNEL_END("score_small_grads_kernel", st);
+  int rc = linear_bwd_data("gemm_score_bwd_e", E, H, d, g_pre, H, W1e, d, nullptr, nullptr, g_e, d, st);     // g_e = g_pre W1e
   if (rc) return rc;
-  rc = linear_bwd_weight(E, H, d, g_pre, H, e, d, dW1e, nullptr, st);                      // dW1e = g_pre^T e
+  rc = linear_bwd_weight("gemm_score_dW1e", E, H, d, g_pre, H, e, d, dW1e, nullptr, st);                      // dW1e = g_pre^T e
   if (rc) return rc;
+  GG_KERNEL_BEGIN("edge_to_node_sums_kernel", st);
   edge_to_node_sums_kernel<64><<<node_grid(N), kNodeThreads, 0, st>>>(N, pl->in_ptr, pl->out_ptr, pl->out_eid, g_pre, gQ);
-  GG_LAUNCH_CHECK("edge_to_node_sums_kernel");
-  rc = linear_bwd_data(N, 2 * H, d, gQ, 2 * H, Wq, d, nullptr, nullptr, g_x, d, st);    // g_x = gQ Wq
+  GG_KERNEL_END("edge_to_node_sums_kernel", st);
+  rc = linear_bwd_data("gemm_score_bwd_x", N, 2 * H, d, gQ, 2 * H, Wq, d, nullptr, nullptr, g_x, d, st);    // g_x = gQ Wq
   if (rc) return rc;
-  return linear_bwd_weight(N, 2 * H, d, gQ, 2 * H, x, d, dWq, nullptr, st);              // dWq = gQ^T x
+  return linear_bwd_weight("gemm_score_dWq", N, 2 * H, d, gQ, 2 * H, x, d, dWq, nullptr, st);              // dWq = gQ^T x
 }
 
 int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx, float* out, void* stream) {
   GG_REQUIRE(rows >= 0 && width > 0, "gather_rows: bad sizes");
   if (rows == 0) return GG_OK;
   GG_REQUIRE(in && idx && out, "gather_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
   int64_t blocks = (rows * width + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, width, in, idx, out);
-  GG_LAUNCH_CHECK("gather_rows_kernel");
+  GG_KERNEL_BEGIN("gather_rows_kernel", st);
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, width, in, idx, out);
+  GG_KERNEL_END("gather_rows_kernel", st);
   return GG_OK;
 }
 

@@ -19,8 +19,15 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return gg::cuda_fail(_e, #call);        \
   } while (0)
 
-#define GG_LAUNCH_CHECK(name)                                      \
+// every kernel launch is bracketed by these two: they count launches (gg_launch_count) and, when
+// profiling is on (gg_profile_enable), time the launch with a CUDA event pair on the launching stream
+void kernel_begin(const char* name, cudaStream_t st);
+void kernel_end(const char* name, cudaStream_t st);
+
+#define GG_KERNEL_BEGIN(name, st) gg::kernel_begin(name, st)
+#define GG_KERNEL_END(name, st)                                    \
   do {                                                             \
+    gg::kernel_end(name, st);                                      \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return gg::cuda_fail(_e, name);         \
   } while (0)

@@ -333,7 +333,7 @@ struct EpiScore {
 
 // ------------------------------------------------------------------------------------ launcher
 template <int BN, bool A_T, bool B_T, bool kStats, bool kBiasGrad, class Epi>
-int launch_gemm(GemmArgs g, const Epi& epi, int splits, cudaStream_t stream) {
+int launch_gemm(const char* tag, GemmArgs g, const Epi& epi, int splits, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0) return GG_OK;
   g.n_tiles = (g.N + BN - 1) / BN;
   const int64_t m_tiles = (g.M + kBM - 1) / kBM;
@@ -348,8 +348,9 @@ int launch_gemm(GemmArgs g, const Epi& epi, int splits, cudaStream_t stream) {
   const int64_t blocks = m_tiles * g.n_tiles;
   if (blocks > 2147483647LL) { set_error("gemm: grid too large"); return GG_ERR_ARG; }
   dim3 grid((unsigned)blocks, (unsigned)splits, 1);
+  GG_KERNEL_BEGIN(tag, stream);
   gemm_ffma_kernel<BN, A_T, B_T, kStats, kBiasGrad, Epi><<<grid, kGemmThreads, 0, stream>>>(g, epi);
-  GG_LAUNCH_CHECK("gemm_ffma_kernel");
+  GG_KERNEL_END(tag, stream);
   return GG_OK;
 }
 

@@ -2,7 +2,11 @@
 // Replaces the structural role of the DGLGraph argument and of dgl.reverse
 // (models/full_graph.py:22, layers/gated_gcn_full.py:115): dgl.reverse keeps edge ids and swaps
 // src/dst, which here is simply "walk the out-edge CSR instead of the in-edge CSR".
+#include <atomic>
+#include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -20,6 +24,34 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
+
+// ---- launch counter + optional per-launch CUDA-event timing (gg_profile_*) ----------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::atomic<int64_t> g_launches{0};
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static thread_local cudaEvent_t g_open_a = nullptr;
+
+void kernel_begin(const char* name, cudaStream_t st) {
+  (void)name;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  cudaEvent_t a;
+  if (cudaEventCreate(&a) != cudaSuccess) { g_open_a = nullptr; return; }
+  cudaEventRecord(a, st);
+  g_open_a = a;
+}
+
+void kernel_end(const char* name, cudaStream_t st) {
+  if (!g_prof_on || g_open_a == nullptr) return;
+  cudaEvent_t b;
+  if (cudaEventCreate(&b) != cudaSuccess) return;
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back({name, g_open_a, b});
+  g_open_a = nullptr;
+}
 
 static bool is_device_ptr(const void* p) {
   cudaPointerAttributes attr;
@@ -46,6 +78,44 @@ extern "C" {
 int gg_version(void) { return 100; }
 
 const char* gg_last_error(void) { return gg::last_error_cstr(); }
+
+int64_t gg_launch_count(void) { return gg::g_launches.load(); }
+
+int gg_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(gg::g_prof_mu);
+  gg::g_prof_on = on != 0;
+  return GG_OK;
+}
+
+int gg_profile_report(char* buf, size_t cap) {
+  GG_REQUIRE(buf && cap > 2, "profile_report: bad buffer");
+  std::lock_guard<std::mutex> lk(gg::g_prof_mu);
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  for (auto& r : gg::g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  gg::g_prof_recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    std::snprintf(line, sizeof line, "%s\"%s\": [%lld, %.6f]", first ? "" : ", ", kv.first.c_str(),
+                  (long long)kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  GG_REQUIRE(out.size() + 1 <= cap, "profile_report: buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return GG_OK;
+}
 
 int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t N, int64_t E, void* stream_, gg_plan_t** out) {
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -55,10 +55,11 @@ class GraphPlan:
             which = self._WHICH[name]
             n = self.num_nodes + 1 if name in ("in_ptr", "out_ptr") else self.num_edges
             out = torch.empty(n, dtype=torch.int32, device=self.device)
-            with torch.cuda.device(self.device):
-                rc = _lib.lib().gg_plan_copy_array(self._handle, which, out.data_ptr(),
-                                                   torch.cuda.current_stream().cuda_stream)
-            _lib.check(rc, "gg_plan_copy_array")
+            if n > 0:
+                with torch.cuda.device(self.device):
+                    rc = _lib.lib().gg_plan_copy_array(self._handle, which, out.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream)
+                _lib.check(rc, "gg_plan_copy_array")
             cache[name] = out
         return cache[name]
 

@@ -33,6 +33,15 @@ typedef struct gg_plan gg_plan_t;
 int gg_version(void);
 const char* gg_last_error(void);
 
+/* ---- instrumentation ------------------------------------------------------------------------
+ * gg_launch_count: number of kernels this library has launched in this process (bench.py's gpu_launches).
+ * gg_profile_enable(1): bracket every launch with a CUDA event pair on the launching stream;
+ * gg_profile_report: synchronise those events, write {"kernel": [launches, total_ms], ...} as JSON text
+ * into buf and clear the records.  The reference has torch.profiler imported but unused (train.py:16). */
+int64_t gg_launch_count(void);
+int gg_profile_enable(int on);
+int gg_profile_report(char* buf, size_t cap);
+
 /* ---- graph plan -------------------------------------------------------------------------
  * Replaces the structure side of the DGLGraph argument of GraphGatedGCNModel.forward
  * (models/full_graph.py:22) and dgl.reverse (layers/gated_gcn_full.py:115).

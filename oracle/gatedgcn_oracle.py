@@ -68,14 +68,20 @@ class OracleGatedGCN(nn.Module):
             self.bn_h = nn.LayerNorm(out_channels)
             self.bn_e = nn.LayerNorm(out_channels)
 
-    def forward(self, src, dst, num_nodes, h, e):
+    def forward(self, src, dst, num_nodes, h, e, probe=None):
+        """`probe` (test aid, a dict): records the smallest |pre-ReLU value| seen, so a test can pick
+        inputs whose ReLU masks cannot flip between fp32 and fp64."""
         h_in, e_in = h, e                                           # :101-102
         A1h, A2h, A3h = self.A_1(h), self.A_2(h), self.A_3(h)       # :107-109
         B1h, B2h, B3e = self.B_1(h), self.B_2(h), self.B_3(e)       # :111-113
 
         # forward message passing, :120-130
         e_ji = u_add_v(src, dst, B1h, B2h) + B3e                    # :120-121
-        e_ji = F.relu(self.bn_e(e_ji))                              # :122-123
+        e_ji = self.bn_e(e_ji)                                      # :122
+        if probe is not None:
+            probe["min_abs_pre"] = min(probe.get("min_abs_pre", 1e30), float(e_ji.detach().abs().min())) \
+                if e_ji.numel() else probe.get("min_abs_pre", 1e30)
+        e_ji = F.relu(e_ji)                                         # :123
         if self.residual:
             e_ji = e_ji + e_in                                      # :124-125
         sigma_f = torch.sigmoid(e_ji)                               # :127
@@ -95,7 +101,10 @@ class OracleGatedGCN(nn.Module):
         h_backward = num_b / (den_b + 1e-6)                         # :143
 
         h = A1h + h_forward + h_backward                            # :145
-        h = F.relu(self.bn_h(h))                                    # :147-149
+        h = self.bn_h(h)                                            # :147
+        if probe is not None:
+            probe["min_abs_pre"] = min(probe.get("min_abs_pre", 1e30), float(h.detach().abs().min()))
+        h = F.relu(h)                                               # :149
         if self.residual:
             h = h + h_in                                            # :151-152
         h = F.dropout(h, self.dropout, training=self.training)      # :154

@@ -122,8 +122,19 @@ def test_layer_matches_oracle(d, batch_norm):
     ours.to(dev)
     src = torch.from_numpy(g.src.astype(np.int64))
     dst = torch.from_numpy(g.dst.astype(np.int64))
-    h = torch.randn(g.num_nodes, d)
-    e = torch.randn(g.num_edges, d)
+    # pick inputs whose pre-ReLU values keep a margin from 0, so no ReLU mask can flip between the fp32
+    # kernels and the fp64 oracle (a single flip moves a weight gradient by one edge's contribution)
+    for attempt in range(50):
+        h = torch.randn(g.num_nodes, d)
+        e = torch.randn(g.num_edges, d)
+        probe = {}
+        with torch.no_grad():
+            ref.double()(src, dst, g.num_nodes, h.double(), e.double(), probe=probe)
+        if probe["min_abs_pre"] > 4e-6:
+            break
+    else:
+        pytest.fail("could not find inputs with a ReLU margin")
+    ref.float()
     gh = torch.randn(g.num_nodes, d)
     ge = torch.randn(g.num_edges, d)
 
