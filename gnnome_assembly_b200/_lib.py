@@ -19,6 +19,7 @@ _i64 = C.c_int64
 SIGNATURES = {
     "gg_version": (_i, []),
     "gg_last_error": (C.c_char_p, []),
+    "gg_set_tc_mode": (_i, [_i]),
     "gg_launch_count": (_i64, []),
     "gg_profile_enable": (_i, [_i]),
     "gg_profile_report": (_i, [C.c_char_p, C.c_size_t]),
@@ -60,6 +61,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        if os.environ.get("GG_TC_MODE") is not None:      # 0 = FFMA everywhere, 1 = tcgen05 3xTF32 where eligible
+            handle.gg_set_tc_mode(int(os.environ["GG_TC_MODE"]))
     return _lib
 
 
@@ -88,3 +91,8 @@ def profile_report():
     buf = C.create_string_buffer(1 << 16)
     check(lib().gg_profile_report(buf, len(buf)), "gg_profile_report")
     return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}
+
+
+def set_tc_mode(mode):
+    """1 (default): tcgen05 3xTF32 GEMM where eligible; 0: FFMA GEMM everywhere.  Returns the previous mode."""
+    return int(lib().gg_set_tc_mode(int(mode)))

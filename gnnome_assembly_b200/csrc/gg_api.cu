@@ -3,6 +3,7 @@
 // caller's stream; every buffer is caller-owned.
 #include "gg_common.cuh"
 #include "gg_gemm_ffma.cuh"
+#include "gg_gemm_tc.cuh"
 #include "gg_layer_kernels.cuh"
 
 namespace gg {
@@ -26,6 +27,9 @@ static unsigned node_grid(int64_t n) {
   return (unsigned)blocks;
 }
 
+// 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
+static int g_tc_mode = 1;
+
 static int pick_splits(int64_t K, int64_t tiles) {
   int64_t want = (2LL * sm_count() + tiles - 1) / tiles;
   int64_t max_by_k = (K + 511) / 512;          // at least 512 reduction rows per split
@@ -41,6 +45,8 @@ static int linear_fwd(const char* tag, int64_t M, int N, int K, const float* X, 
   GemmArgs g{};
   g.A = X; g.lda = ldx; g.B = W; g.ldb = ldw; g.M = M; g.N = N; g.K = K;
   EpiBias epi{Y, ldy, b, relu};
+  if (g_tc_mode && tc::eligible(false, false, M, N, K, ldx, ldw, X, W))
+    return tc::launch<false, false, false, false>(tag, X, ldx, W, ldw, M, N, K, 1, nullptr, nullptr, epi, sm_count(), st);
   if (N >= 128) return launch_gemm<128, false, true, false, false>(tag, g, epi, 1, st);
   if (N > 32) return launch_gemm<64, false, true, false, false>(tag, g, epi, 1, st);
   return launch_gemm<32, false, true, false, false>(tag, g, epi, 1, st);
@@ -52,6 +58,8 @@ static int linear_bwd_data(const char* tag, int64_t M, int N, int K, const float
   GemmArgs g{};
   g.A = dY; g.lda = lddy; g.B = W; g.ldb = ldw; g.M = M; g.N = K; g.K = N;
   EpiAddMask epi{dX, lddx, addend, mask};
+  if (g_tc_mode && tc::eligible(false, true, M, K, N, lddy, ldw, dY, W))
+    return tc::launch<false, true, false, false>(tag, dY, lddy, W, ldw, M, K, N, 1, nullptr, nullptr, epi, sm_count(), st);
   if (K >= 128) return launch_gemm<128, false, false, false, false>(tag, g, epi, 1, st);
   if (K > 32) return launch_gemm<64, false, false, false, false>(tag, g, epi, 1, st);
   return launch_gemm<32, false, false, false, false>(tag, g, epi, 1, st);
@@ -68,6 +76,14 @@ static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const flo
   g.bias_grad = db;
   EpiAtomic epi{dW, (int64_t)K};
   const int64_t m_tiles = (N + kBM - 1) / kBM;
+  if (g_tc_mode && tc::eligible(true, true, N, K, M, lddy, ldx, dY, X)) {
+    const int64_t tiles = m_tiles * (K / tc::BN);
+    int64_t want = (sm_count() + tiles - 1) / tiles;
+    const int64_t max_by_k = (M + 1023) / 1024;
+    if (want > max_by_k) want = max_by_k;
+    if (want < 1) want = 1;
+    return tc::launch<true, true, false, true>(tag, dY, lddy, X, ldx, N, K, M, (int)want, nullptr, db, epi, sm_count(), st);
+  }
   if (K >= 128) return launch_gemm<128, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles * ((K + 127) / 128)), st);
   if (K > 32) return launch_gemm<64, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles), st);
   return launch_gemm<32, true, false, false, true>(tag, g, epi, pick_splits(M, m_tiles), st);
@@ -91,7 +107,11 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     g.col_stats = stats;
     EpiEdgeGate epi{t, D, b3, P, pl->src, pl->dst};
     constexpr int BN = D >= 128 ? 128 : 64;
-    rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
+    if (g_tc_mode && tc::eligible(false, false, E, D, D, D, D, e_in, B3))
+      rc = tc::launch<false, false, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", e_in, D, B3, D, E, D, D, 1, stats,
+                                                                   nullptr, epi, sm_count(), st);
+    else
+      rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
     if (rc) return rc;
   }
   GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
@@ -235,6 +255,12 @@ using namespace gg;
   } while (0)
 
 extern "C" {
+
+int gg_set_tc_mode(int mode) {
+  const int old = g_tc_mode;
+  g_tc_mode = mode ? 1 : 0;
+  return old;
+}
 
 int gg_linear_fwd(int64_t M, int N, int K, const float* X, const float* W, const float* b, int relu, float* Y,
                   void* stream) {

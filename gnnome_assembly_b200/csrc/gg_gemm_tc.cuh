@@ -1,0 +1,473 @@
+// gg_gemm_tc.cuh — 3xTF32 GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM, operands staged by TMA with 128-byte swizzle), with the same pluggable epilogues as the FFMA GEMM.
+//
+// Why 3xTF32: the reference runs its projections in true fp32 (torch allow_tf32=False,
+// layers/gated_gcn_full.py:44,107-113) and plain TF32 misses the 1e-4 logit tolerance.
+// Each fp32 operand x is split as x = hi + lo with hi = x with the low 13 mantissa bits cleared (exactly a
+// TF32 number) and lo = x - hi (exact in fp32); D = A_hi B_hi + A_lo B_hi + A_hi B_lo drops only the
+// lo*lo term (~2^-20 relative).  TMA lands the raw fp32 tile; four "splitter" warps rewrite it in place
+// as hi and write lo to a second buffer with the same (swizzled) byte layout, so the split is layout
+// agnostic; one thread issues the 3 MMAs per K step.
+//
+// Tile: 128 (M) x 128 (N) x 32 (K, = one 128-byte swizzle row of fp32), 3-stage mbarrier pipeline,
+// persistent CTAs (one per SM), two TMEM accumulators (2 x 128 columns) so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+//   warp 0      TMA producer          warp 1   MMA issuer        warp 2   TMEM allocator
+//   warps 4-7   hi/lo splitter        warps 8-11  epilogue (TMEM -> registers -> smem -> coalesced rows)
+// Operand layouts (template flags): K-major = the reduction index is contiguous in global memory
+// (A[M,K] row-major, nn.Linear W[N,K]); MN-major = the M / N index is contiguous (B[K,N] in bwd-data,
+// both operands in weight gradients).  Descriptor encodings follow CUTLASS cute/arch/mma_sm100_desc.hpp.
+#pragma once
+#include <cuda.h>
+
+#include "gg_common.cuh"
+#include "gg_gemm_ffma.cuh"
+
+namespace gg {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
+constexpr int STG_LD = 36;                        // epilogue staging row stride (floats): 32 + 4 pad
+constexpr int STAGING_BYTES = BM * STG_LD * 4;    // 18 KB
+constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 warps][128 cols][sum, sumsq] doubles
+constexpr int BIAS_BYTES = BM * 4;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + BAR_BYTES;
+constexpr int THREADS = 384;
+constexpr int TMEM_COLS = 256;
+
+struct Args {
+  int64_t M; int N; int64_t K;
+  int m_tiles, n_tiles, splits;
+  int64_t k_chunk;           // multiple of BK
+  double* col_stats;         // kStats: [2N]
+  float* bias_grad;          // kBiasGrad (A MN-major only): [M] sums of A over k
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), LBO [16,30),
+// SBO [32,46) (all >> 4), version = 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64)
+// K-major operands use SWIZZLE_128B (16-byte chunks permuted over 8 rows).  MN-major TF32 operands
+// have exactly one legal layout, SWIZZLE_128B_BASE32B = 1 (32-byte chunks permuted over 4 rows, CuTe
+// Layout_MN_SW128_32B_Atom; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+template <bool MN>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  // K-major : rows 128 B apart, 8-row groups 1 KB apart (SBO); LBO unused (1)
+  // MN-major: 32-wide MN blocks 4 KB apart (LBO, one TMA box of 32 k-rows each); 4-row K groups 512 B apart (SBO)
+  constexpr uint32_t lbo_bytes = MN ? 4096 : 16, sbo_bytes = MN ? 512 : 1024;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(MN ? 1 : 2) << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------- the kernel
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stage0 = base;
+  float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
+  double* sstat = reinterpret_cast<double*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES);
+  float* sbias = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES);
+  const uint32_t bars = base + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + 128);
+  auto full_raw = [&](int s) { return bars + 8u * s; };
+  auto full_split = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tmem_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+  auto tmem_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_split(s), 128); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 8) {
+    for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 128) sstat[i] = 0.0;
+    if (threadIdx.x - 256 < BM) sbias[threadIdx.x - 256] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (m_tile, n_tile, split): n fastest so that consecutive CTAs share the A rows in L2
+  auto decode = [&](int64_t w, int& mt, int& nt, int& sp) {
+    nt = (int)(w % g.n_tiles);
+    const int64_t r = w / g.n_tiles;
+    mt = (int)(r % g.m_tiles);
+    sp = (int)(r / g.m_tiles);
+  };
+  auto k_range = [&](int sp, int64_t& kbeg, int& nkb) {
+    kbeg = (int64_t)sp * g.k_chunk;
+    int64_t kend = kbeg + g.k_chunk;
+    if (kend > g.K) kend = g.K;
+    nkb = (int)((kend - kbeg + BK - 1) / BK);
+  };
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int mt, nt, sp; decode(w, mt, nt, sp);
+        int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty(s), ph ^ 1u);
+          const uint32_t st = stage0 + s * STAGE_BYTES;
+          mbar_expect_tx(full_raw(s), 2 * TILE_BYTES);
+          const int k0 = (int)(kbeg + (int64_t)kb * BK);
+          if constexpr (!A_MN) {
+            tma_load_2d(st, &tmA, full_raw(s), k0, mt * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &tmA, full_raw(s), mt * BM + 32 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(st + 2 * TILE_BYTES, &tmB, full_raw(s), k0, nt * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+      for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int mt, nt, sp; decode(w, mt, nt, sp);
+        int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+        mbar_wait(tmem_empty(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_split(s), ph);
+          tc_fence_after();
+          const uint32_t st = stage0 + s * STAGE_BYTES;
+          // K step (8 tf32): K-major = 32 B inside the swizzle row; MN-major = 8 k-rows = 1 KB
+          const uint64_t a_hi = make_desc<A_MN>(st);
+          const uint64_t a_lo = make_desc<A_MN>(st + TILE_BYTES);
+          const uint64_t b_hi = make_desc<B_MN>(st + 2 * TILE_BYTES);
+          const uint64_t b_lo = make_desc<B_MN>(st + 3 * TILE_BYTES);
+          constexpr uint64_t a_step = A_MN ? (1024 >> 4) : (32 >> 4);
+          constexpr uint64_t b_step = B_MN ? (1024 >> 4) : (32 >> 4);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+            umma_tf32(d_tmem, a_lo + ks * a_step, b_hi + ks * b_step, idesc, first);   // small terms first
+            umma_tf32(d_tmem, a_hi + ks * a_step, b_lo + ks * b_step, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + ks * a_step, b_hi + ks * b_step, idesc, 1u);
+          }
+          umma_commit(empty(s));                       // frees the stage when these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tmem_full(acc));                   // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================ hi/lo splitter (128 threads)
+    const int t = threadIdx.x - 128;
+    int s = 0; uint32_t ph = 0;
+    float4 bsum[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, sp; decode(w, mt, nt, sp);
+      int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_raw(s), ph);
+        uint8_t* st = gen + s * STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            const int q = t + 128 * i;
+            const float4 x = hi[q];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+            hi[q] = h;
+            lo[q] = l;
+            if constexpr (kBiasGrad && A_MN) {
+              // A tile is [k][m] in 4 boxes of 32 m; float4 q lives in box q/256 (= i/2), its m chunk is fixed per thread
+              if (op == 0) { bsum[i >> 1].x += x.x; bsum[i >> 1].y += x.y; bsum[i >> 1].z += x.z; bsum[i >> 1].w += x.w; }
+            }
+          }
+        }
+        proxy_fence_async();                           // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_split(s));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      if constexpr (kBiasGrad && A_MN) {
+        if (g.bias_grad != nullptr && nt == 0) {
+          // 128B_ATOM_32B swizzle: physical 32-byte chunk j' = (t % 8) / 2 of k-row r (r % 4 = (t / 8) % 4)
+          // holds logical 32-byte chunk j' ^ (r % 4); the 16-byte half inside it is unchanged
+          const int c = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t m = (int64_t)mt * BM + 32 * j + 4 * c;
+            if (m < g.M) {
+              atomicAdd(g.bias_grad + m + 0, bsum[j].x); atomicAdd(g.bias_grad + m + 1, bsum[j].y);
+              atomicAdd(g.bias_grad + m + 2, bsum[j].z); atomicAdd(g.bias_grad + m + 3, bsum[j].w);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================================================ epilogue (128 threads, TMEM lanes = rows)
+    const int t = threadIdx.x - 256;
+    const int ew = warp - 8;                            // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, sp; decode(w, mt, nt, sp);
+      mbar_wait(tmem_full(acc), acc_ph);
+      tc_fence_after();
+      const int64_t m0 = (int64_t)mt * BM;
+      const int n0 = nt * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 32 * c), v);
+        if (c == BN / 32 - 1) {                         // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tmem_empty(acc));
+        }
+        float* row = staging + t * STG_LD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        const int c4 = (t & 7) * 4;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int r = p * 16 + (t >> 3);
+          const float4 x = *reinterpret_cast<const float4*>(staging + r * STG_LD + c4);
+          float a[4] = {x.x, x.y, x.z, x.w};
+          const int64_t m = m0 + r;
+          const int n = n0 + 32 * c + c4;
+          const bool valid = (m < g.M) && (n < g.N);
+          epi.template apply<4>(m, n, a, valid);
+          if constexpr (kStats) {
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { s1[j] += (double)a[j]; s2[j] += (double)a[j] * (double)a[j]; }
+            }
+          }
+        }
+        if constexpr (kStats) {
+          // lanes l, l+8, l+16, l+24 own the same 4 columns
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sstat[(ew * BN + 32 * c + c4 + j) * 2 + 0] += s1[j];
+              sstat[(ew * BN + 32 * c + c4 + j) * 2 + 1] += s2[j];
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if constexpr (kStats) {
+        // flush this tile's column statistics (the n tile can change between work items)
+        const int n = n0 + t;
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a += sstat[(q * BN + t) * 2]; b += sstat[(q * BN + t) * 2 + 1]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sstat[(q * BN + t) * 2] = 0.0; sstat[(q * BN + t) * 2 + 1] = 0.0; }
+        if (n < g.N) { atomicAdd(g.col_stats + n, a); atomicAdd(g.col_stats + g.N + n, b); }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch `ld` floats,
+// box = 32 floats (128 B, SWIZZLE_128B) x box_rows
+inline int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_rows,
+                    bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gnnome_b200: cuTensorMapEncodeTiled not available"); return GG_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gnnome_b200: cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return GG_ERR_CUDA; }
+  return GG_OK;
+}
+
+// K-major operands need K % 32 == 0 (whole 128-byte swizzle rows); MN-major ones take any K (zero fill)
+inline bool eligible(bool a_mn, bool b_mn, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, const void* A,
+                     const void* B) {
+  if (M <= 0 || K <= 0 || N % BN != 0 || lda % 4 != 0 || ldb % 4 != 0) return false;
+  if ((!a_mn || !b_mn) && K % BK != 0) return false;
+  if (a_mn && M % 4 != 0) return false;
+  return (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0);
+}
+
+// C[M,N] = sum_k A(m,k) B(k,n).  A_MN: A stored [K, M] (lda) else [M, K];  B_MN: B stored [K, N] (ldb) else [N, K].
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi>
+int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
+           int splits, double* col_stats, float* bias_grad, const Epi& epi, int num_sms, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (A_MN) rc = make_map(&tmA, A, M, K, lda, 32, true); else rc = make_map(&tmA, A, K, M, lda, BM, false);
+  if (rc) return rc;
+  if (B_MN) rc = make_map(&tmB, B, N, K, ldb, 32, true); else rc = make_map(&tmB, B, K, N, ldb, BN, false);
+  if (rc) return rc;
+  Args g{};
+  g.M = M; g.N = N; g.K = K;
+  g.m_tiles = (int)((M + BM - 1) / BM);
+  g.n_tiles = N / BN;
+  if (splits < 1) splits = 1;
+  int64_t chunk = (K + splits - 1) / splits;
+  chunk = ((chunk + BK - 1) / BK) * BK;
+  g.k_chunk = chunk;
+  g.splits = (int)((K + chunk - 1) / chunk);
+  g.col_stats = col_stats;
+  g.bias_grad = bias_grad;
+  const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
+  const int grid = (int)(work < num_sms ? work : num_sms);
+  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi>;
+  static bool attr_set = false;      // one static per template instantiation
+  if (!attr_set) {
+    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  GG_KERNEL_BEGIN(tag, st);
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, g, epi);
+  GG_KERNEL_END(tag, st);
+  return GG_OK;
+}
+
+}  // namespace tc
+}  // namespace gg

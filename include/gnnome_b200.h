@@ -38,6 +38,9 @@ const char* gg_last_error(void);
  * gg_profile_enable(1): bracket every launch with a CUDA event pair on the launching stream;
  * gg_profile_report: synchronise those events, write {"kernel": [launches, total_ms], ...} as JSON text
  * into buf and clear the records.  The reference has torch.profiler imported but unused (train.py:16). */
+/* gg_set_tc_mode(1) (default): projections with N % 128 == 0 run on the tcgen05 3xTF32 tensor-core kernel;
+ * gg_set_tc_mode(0): true-fp32 FFMA kernel everywhere.  Returns the previous mode. */
+int gg_set_tc_mode(int mode);
 int64_t gg_launch_count(void);
 int gg_profile_enable(int on);
 int gg_profile_report(char* buf, size_t cap);

@@ -60,9 +60,19 @@ def test_plan_rejects_bad_index():
 
 
 # ------------------------------------------------------------------------------------------ linear
+@pytest.fixture(params=[1, 0], ids=["tc", "ffma"])
+def tc_mode(request):
+    """Run a test on the tcgen05 3xTF32 GEMM path (default) and on the FFMA path."""
+    from gnnome_assembly_b200 import _lib
+    old = _lib.set_tc_mode(request.param)
+    yield request.param
+    _lib.set_tc_mode(old)
+
+
 @pytest.mark.parametrize("M,N,K", [(1, 16, 4), (130, 128, 20), (257, 64, 16), (1000, 640, 128), (300, 20, 256),
-                                    (5000, 256, 256), (129, 128, 64)])
-def test_linear_fwd_bwd(M, N, K):
+                                    (5000, 256, 256), (129, 128, 64), (128, 128, 32), (40000, 128, 128),
+                                    (33333, 256, 1280), (777, 1280, 256)])
+def test_linear_fwd_bwd(M, N, K, tc_mode):
     dev = _dev()
     from gnnome_assembly_b200 import functional as GF
     torch.manual_seed(M + N + K)
@@ -106,7 +116,7 @@ def _rand_graph(n, m, seed, isolated=0.1):
 
 @pytest.mark.parametrize("d", [64, 128, 256])
 @pytest.mark.parametrize("batch_norm", [True, False])
-def test_layer_matches_oracle(d, batch_norm):
+def test_layer_matches_oracle(d, batch_norm, tc_mode):
     dev = _dev()
     O = _oracle()
     import gnnome_assembly_b200 as gg
@@ -215,7 +225,7 @@ def _run_model(g, state_dict, dev, grads=True):
 
 
 @pytest.mark.parametrize("name", ["ref_rand_d64_L2_bn", "ref_rand_d64_L2_ln", "ref_asm_d128_L3_bn"])
-def test_model_matches_reference_golden(golden_dir, name):
+def test_model_matches_reference_golden(golden_dir, name, tc_mode):
     dev = _dev()
     O = _oracle()
     g = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
@@ -226,7 +236,7 @@ def test_model_matches_reference_golden(golden_dir, name):
     assert O.grads_close(out["grads"], g["grads"], rtol=2e-3, atol_frac=1e-5) == []
 
 
-def test_model_checkpoint_golden(golden_dir, ckpt_path):
+def test_model_checkpoint_golden(golden_dir, ckpt_path, tc_mode):
     """Config 3 of BASELINE.json at fixture size: shipped model_15xchr19.pt (d=256, L=16) on a chr21-like graph."""
     dev = _dev()
     O = _oracle()
