@@ -238,8 +238,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_ffma_kernel(GemmArgs g, 
 
 // ------------------------------------------------------------------------------------ epilogues
 // Y = acc + bias (optional) ; optional ReLU ; store
+// (tensor-core kernel: `Pre` holds the epilogue's global operands for one float4 of output, fetched by
+//  prefetch() a chunk ahead; apply_pre() finishes the element; kIdx = needs the row's src/dst node ids)
 struct EpiBias {
   float* C; int64_t ldc; const float* bias; int relu;
+  static constexpr bool kIdx = false;
+  struct Pre {};
+  __device__ __forceinline__ void prefetch(Pre&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre&, bool valid) const {
+    apply<4>(m, n, acc, valid);
+  }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
     if (!valid) return;
@@ -256,6 +264,20 @@ struct EpiBias {
 // dX = acc (+ addend) ; zero where mask <= 0 ; store          (bwd-data, ReLU backward fused)
 struct EpiAddMask {
   float* C; int64_t ldc; const float* addend; const float* mask;
+  static constexpr bool kIdx = false;
+  struct Pre { float4 add, msk; };
+  __device__ __forceinline__ void prefetch(Pre& p, int64_t m, int n, int, int) const {
+    p.add = addend ? __ldg(reinterpret_cast<const float4*>(addend + m * ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    p.msk = mask ? __ldg(reinterpret_cast<const float4*>(mask + m * ldc + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre& p, bool valid) const {
+    if (!valid) return;
+    acc[0] = p.msk.x > 0.f ? acc[0] + p.add.x : 0.f;
+    acc[1] = p.msk.y > 0.f ? acc[1] + p.add.y : 0.f;
+    acc[2] = p.msk.z > 0.f ? acc[2] + p.add.z : 0.f;
+    acc[3] = p.msk.w > 0.f ? acc[3] + p.add.w : 0.f;
+    *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
     if (!valid) return;
@@ -274,6 +296,12 @@ struct EpiAddMask {
 // split-K weight gradient: C += acc with fp32 atomics (C zeroed by the caller)
 struct EpiAtomic {
   float* C; int64_t ldc;
+  static constexpr bool kIdx = false;
+  struct Pre {};
+  __device__ __forceinline__ void prefetch(Pre&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre&, bool valid) const {
+    apply<4>(m, n, acc, valid);
+  }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
     if (!valid) return;
@@ -286,6 +314,21 @@ struct EpiAtomic {
 //   t[i, c] = (B3 e_i + b3)[c] + B1h[src_i, c] + B2h[dst_i, c];  P rows are [A1h|A2h|A3h|B1h|B2h]
 struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
+  static constexpr bool kIdx = true;
+  struct Pre { float4 p1, p2; };
+  __device__ __forceinline__ void prefetch(Pre& p, int64_t, int n, int s, int v) const {
+    p.p1 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)s * (5 * d) + 3 * d + n));
+    p.p2 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)v * (5 * d) + 4 * d + n));
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre& p, bool valid) const {
+    if (!valid) return;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + n));
+    acc[0] = (p.p1.x + p.p2.x) + (acc[0] + b.x);
+    acc[1] = (p.p1.y + p.p2.y) + (acc[1] + b.y);
+    acc[2] = (p.p1.z + p.p2.z) + (acc[2] + b.z);
+    acc[3] = (p.p1.w + p.p2.w) + (acc[3] + b.w);
+    *reinterpret_cast<float4*>(t + m * d + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
     static_assert(GW == 4, "edge gate epilogue runs on 128/64-wide tiles");

@@ -13,7 +13,9 @@
 // persistent CTAs (one per SM), two TMEM accumulators (2 x 128 columns) so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 //   warp 0      TMA producer          warp 1   MMA issuer        warp 2   TMEM allocator
-//   warps 4-7   hi/lo splitter        warps 8-11  epilogue (TMEM -> registers -> smem -> coalesced rows)
+//   warps 4-7   hi/lo splitter        warps 8-15  epilogue, two groups of 4 warps, 64 columns each
+//                                     (TMEM -> registers -> smem -> coalesced row segments, operands of the
+//                                      fused epilogue prefetched one chunk ahead)
 // Operand layouts (template flags): K-major = the reduction index is contiguous in global memory
 // (A[M,K] row-major, nn.Linear W[N,K]); MN-major = the M / N index is contiguous (B[K,N] in bwd-data,
 // both operands in weight gradients).  Descriptor encodings follow CUTLASS cute/arch/mma_sm100_desc.hpp.
@@ -30,13 +32,13 @@ constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one s
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
-constexpr int STG_LD = 36;                        // epilogue staging row stride (floats): 32 + 4 pad
-constexpr int STAGING_BYTES = BM * STG_LD * 4;    // 18 KB
-constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 warps][128 cols][sum, sumsq] doubles
-constexpr int BIAS_BYTES = BM * 4;
+constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
+constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
+constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
+constexpr int BIAS_BYTES = 2 * 2 * BM * 4;        // per epilogue group: src / dst node id of the tile's 128 rows
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + BAR_BYTES;
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;
 constexpr int TMEM_COLS = 256;
 
 struct Args {
@@ -106,6 +108,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), LBO [16,30),
 // SBO [32,46) (all >> 4), version = 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64)
 // K-major operands use SWIZZLE_128B (16-byte chunks permuted over 8 rows).  MN-major TF32 operands
@@ -141,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage0 = base;
   float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
   double* sstat = reinterpret_cast<double*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES);
-  float* sbias = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES);
+  int* sidx = reinterpret_cast<int*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES);
   const uint32_t bars = base + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + 128);
   auto full_raw = [&](int s) { return bars + 8u * s; };
@@ -155,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_split(s), 128); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -163,8 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 8) {
-    for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 128) sstat[i] = 0.0;
-    if (threadIdx.x - 256 < BM) sbias[threadIdx.x - 256] = 0.f;
+    for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 256) sstat[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -306,39 +320,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 8) {
-    // ================================================================ epilogue (128 threads, TMEM lanes = rows)
-    const int t = threadIdx.x - 256;
-    const int ew = warp - 8;                            // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+    // ================================================================ epilogue (2 groups x 128 threads)
+    // group grp owns accumulator columns [64 grp, 64 grp + 64), 4 chunks of 16 columns.  Per chunk: every
+    // thread pulls its row (TMEM lane) out of TMEM, parks it in the group's staging tile, then the group
+    // walks the tile row-wise (4 threads x float4 = one 64-byte row segment) so that all global traffic of
+    // the fused epilogue is coalesced.  The epilogue's global operands for chunk q+1 are prefetched into
+    // registers before chunk q is processed (double buffer), the tile's src/dst ids one tile ahead.
+    const int grp = (warp - 8) >> 2;
+    const int ew = warp & 3;                            // TMEM lanes 32*ew .. 32*ew+31
+    const int tg = (threadIdx.x - 256) & 127;           // thread in group == accumulator row of the tile
+    const uint32_t bar_id = 1 + grp;
+    float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
+    int* s_src = sidx + grp * 2 * BM;
+    int* s_dst = s_src + BM;
+    const int c4 = (tg & 3) * 4;                        // column offset of this thread inside a chunk
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    using Pre = typename Epi::Pre;
+    Pre pre[2][4];
+
+    auto prefetch = [&](Pre (&dst)[4], int mt_, int nt_, int q) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int r = p * 32 + (tg >> 2);
+        int64_t m = (int64_t)mt_ * BM + r;
+        if (m >= g.M) m = g.M - 1;
+        const int n = nt_ * BN + 64 * grp + EC * q + c4;
+        int sv = 0, dv = 0;
+        if constexpr (Epi::kIdx) { sv = s_src[r]; dv = s_dst[r]; }
+        epi.prefetch(dst[p], m, n, sv, dv);
+      }
+    };
+    auto load_idx = [&](int mt_, int& sv, int& dv) {
+      if constexpr (Epi::kIdx) {
+        int64_t m = (int64_t)mt_ * BM + tg;
+        if (m >= g.M) m = g.M - 1;
+        sv = __ldg(epi.src + m);
+        dv = __ldg(epi.dst + m);
+      }
+    };
+
     int acc = 0; uint32_t acc_ph = 0;
-    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int mt, nt, sp; decode(w, mt, nt, sp);
+    int64_t w = blockIdx.x;
+    int mt = 0, nt = 0, sp = 0;
+    if (w < total_work) {
+      decode(w, mt, nt, sp);
+      int sv = 0, dv = 0;
+      load_idx(mt, sv, dv);
+      if constexpr (Epi::kIdx) { s_src[tg] = sv; s_dst[tg] = dv; }
+      group_bar();
+      prefetch(pre[0], mt, nt, 0);
+    }
+    for (; w < total_work; w += gridDim.x) {
+      const int64_t wn = w + gridDim.x;
+      int mtn = 0, ntn = 0, spn = 0, nsv = 0, ndv = 0;
+      if (wn < total_work) { decode(wn, mtn, ntn, spn); load_idx(mtn, nsv, ndv); }
       mbar_wait(tmem_full(acc), acc_ph);
       tc_fence_after();
       const int64_t m0 = (int64_t)mt * BM;
-      const int n0 = nt * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 32 * c), v);
-        if (c == BN / 32 - 1) {                         // accumulator fully read: hand it back to the MMA warp
+      const int n0 = nt * BN + 64 * grp;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // prefetch the operands of the next chunk (or of the next tile's first chunk)
+        if (q < 3) {
+          prefetch(pre[(q + 1) & 1], mt, nt, q + 1);
+        } else if (wn < total_work) {
+          if constexpr (Epi::kIdx) { s_src[tg] = nsv; s_dst[tg] = ndv; group_bar(); }
+          prefetch(pre[0], mtn, ntn, 0);
+        }
+        float v[EC];
+        tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q), v);
+        if (q == 3) {                                   // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(tmem_empty(acc));
         }
-        float* row = staging + t * STG_LD;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = 0; j < 4; ++j)
+          stg[tg * 4 + (j ^ ((tg >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        group_bar();
         double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-        const int c4 = (t & 7) * 4;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int r = p * 16 + (t >> 3);
-          const float4 x = *reinterpret_cast<const float4*>(staging + r * STG_LD + c4);
+        for (int p = 0; p < 4; ++p) {
+          const int r = p * 32 + (tg >> 2);
+          const float4 x = stg[r * 4 + ((tg & 3) ^ ((r >> 1) & 3))];
           float a[4] = {x.x, x.y, x.z, x.w};
           const int64_t m = m0 + r;
-          const int n = n0 + 32 * c + c4;
+          const int n = n0 + EC * q + c4;
           const bool valid = (m < g.M) && (n < g.N);
-          epi.template apply<4>(m, n, a, valid);
+          epi.apply_pre(m, n, a, pre[q & 1][p], valid);
           if constexpr (kStats) {
             if (valid) {
 #pragma unroll
@@ -347,34 +415,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if constexpr (kStats) {
-          // lanes l, l+8, l+16, l+24 own the same 4 columns
+          // lanes l, l+4, ..., l+28 own the same 4 columns
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+              s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
           }
-          if (lane < 8) {
+          if (lane < 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              sstat[(ew * BN + 32 * c + c4 + j) * 2 + 0] += s1[j];
-              sstat[(ew * BN + 32 * c + c4 + j) * 2 + 1] += s2[j];
+              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 0] += s1[j];
+              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 1] += s2[j];
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        group_bar();
       }
       if constexpr (kStats) {
         // flush this tile's column statistics (the n tile can change between work items)
-        const int n = n0 + t;
         double a = 0.0, b = 0.0;
+        const int col = 64 * grp + (tg & 63);
+        if (tg < 64) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { a += sstat[(q * BN + t) * 2]; b += sstat[(q * BN + t) * 2 + 1]; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int qq = 0; qq < 4; ++qq) { a += sstat[(qq * BN + col) * 2]; b += sstat[(qq * BN + col) * 2 + 1]; }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { sstat[(q * BN + t) * 2] = 0.0; sstat[(q * BN + t) * 2 + 1] = 0.0; }
-        if (n < g.N) { atomicAdd(g.col_stats + n, a); atomicAdd(g.col_stats + g.N + n, b); }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int qq = 0; qq < 4; ++qq) { sstat[(qq * BN + col) * 2] = 0.0; sstat[(qq * BN + col) * 2 + 1] = 0.0; }
+          const int n = nt * BN + col;
+          if (n < g.N) { atomicAdd(g.col_stats + n, a); atomicAdd(g.col_stats + g.N + n, b); }
+        }
+        group_bar();
       }
+      mt = mtn; nt = ntn; sp = spn;
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   }

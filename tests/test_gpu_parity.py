@@ -86,9 +86,12 @@ def test_linear_fwd_bwd(M, N, K, tc_mode):
     y2 = torch.nn.functional.linear(x2, W2, b2)
     y2.backward(g.double())
     rel = _oracle().rel_err
-    assert rel(y, y2) < 1e-5
-    assert rel(x.grad, x2.grad) < 1e-5
-    assert rel(W.grad, W2.grad) < 2e-5
+    # FFMA path: fp32 rounding only.  tcgen05 3xTF32 path: ~2^-20 per product plus the tensor core's
+    # truncating fp32 accumulation, which grows with the number of K steps per accumulator.
+    tol = 6e-5 if tc_mode else 1e-5
+    assert rel(y, y2) < tol
+    assert rel(x.grad, x2.grad) < tol
+    assert rel(W.grad, W2.grad) < 2 * tol
     assert rel(b.grad, b2.grad) < 2e-5
 
 
