@@ -29,6 +29,7 @@ static unsigned node_grid(int64_t n) {
 
 // 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
 static int g_tc_mode = 1;
+namespace tc { int& tc_raw_hi_ref() { static int v = 1; return v; } }
 
 static int pick_splits(int64_t K, int64_t tiles) {
   int64_t want = (2LL * sm_count() + tiles - 1) / tiles;
@@ -257,8 +258,11 @@ using namespace gg;
 extern "C" {
 
 int gg_set_tc_mode(int mode) {
-  const int old = g_tc_mode;
+  const int old = g_tc_mode ? (tc::tc_raw_hi_ref() ? 2 : 1) : 0;
   g_tc_mode = mode ? 1 : 0;
+  // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (measured: identical results with and
+  // without rewriting hi in place), so by default the TMA-landed tile is the hi operand; 2 forces the rewrite
+  tc::tc_raw_hi_ref() = (mode == 2) ? 0 : 1;
   return old;
 }
 

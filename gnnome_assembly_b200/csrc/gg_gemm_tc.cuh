@@ -28,6 +28,9 @@
 namespace gg {
 namespace tc {
 
+int& tc_raw_hi_ref();
+inline int tc_raw_hi() { return tc_raw_hi_ref(); }
+
 constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
@@ -47,6 +50,7 @@ struct Args {
   int64_t k_chunk;           // multiple of BK
   double* col_stats;         // kStats: [2N]
   float* bias_grad;          // kBiasGrad (A MN-major only): [M] sums of A over k
+  int raw_hi;                // 1: leave the TMA-landed fp32 tile as the hi operand (tensor core drops the low bits)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -289,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
             h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-            hi[q] = h;
+            if (!g.raw_hi) hi[q] = h;
             lo[q] = l;
             if constexpr (kBiasGrad && A_MN) {
               // A tile is [k][m] in 4 boxes of 32 m; float4 q lives in box q/256 (= i/2), its m chunk is fixed per thread
@@ -529,6 +533,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   g.splits = (int)((K + chunk - 1) / chunk);
   g.col_stats = col_stats;
   g.bias_grad = bias_grad;
+  g.raw_hi = tc_raw_hi();
   const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
   const int grid = (int)(work < num_sms ? work : num_sms);
   auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi>;

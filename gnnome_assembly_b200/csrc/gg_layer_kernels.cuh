@@ -126,24 +126,42 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
       const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
-      for (int j = 0; j < cnt; ++j) {
-        const int64_t i = base + j;
-        const int64_t s = __shfl_sync(0xffffffffu, my_s, j);
-        Row<D> x, ein, a2;
-        x.load_stream(t + i * D, lane);
-        ein.load_stream(e_in + i * D, lane);
-        a2.load(P + s * (5 * D) + D, lane);
-        nrm.normalize(x);
+      for (int j = 0; j < cnt; j += 2) {
+        const bool two = (j + 1) < cnt;
+        const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
+        const int64_t sa = __shfl_sync(0xffffffffu, my_s, j);
+        const int64_t sb = __shfl_sync(0xffffffffu, my_s, two ? j + 1 : j);
+        Row<D> x0, ein0, a20, x1, ein1, a21;
+        x0.load_stream(t + i0 * D, lane);
+        ein0.load_stream(e_in + i0 * D, lane);
+        a20.load(P + sa * (5 * D) + D, lane);
+        x1.load_stream(t + i1 * D, lane);
+        ein1.load_stream(e_in + i1 * D, lane);
+        a21.load(P + sb * (5 * D) + D, lane);
+        nrm.normalize(x0);
+        nrm.normalize(x1);
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
-          const float nv = x.v[k] * nrm.gamma[k] + nrm.beta[k];
-          const float eo = fmaxf(nv, 0.f) + (residual ? ein.v[k] : 0.f);
-          x.v[k] = eo;
+          const float nv = x0.v[k] * nrm.gamma[k] + nrm.beta[k];
+          const float eo = fmaxf(nv, 0.f) + (residual ? ein0.v[k] : 0.f);
+          x0.v[k] = eo;
           const float sg = sigmoidf_(eo);
-          num.v[k] = fmaf(sg, a2.v[k], num.v[k]);
+          num.v[k] = fmaf(sg, a20.v[k], num.v[k]);
           den.v[k] += sg;
         }
-        x.store(e_out + i * D, lane);
+        x0.store(e_out + i0 * D, lane);
+        if (two) {
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const float nv = x1.v[k] * nrm.gamma[k] + nrm.beta[k];
+            const float eo = fmaxf(nv, 0.f) + (residual ? ein1.v[k] : 0.f);
+            x1.v[k] = eo;
+            const float sg = sigmoidf_(eo);
+            num.v[k] = fmaf(sg, a21.v[k], num.v[k]);
+            den.v[k] += sg;
+          }
+          x1.store(e_out + i1 * D, lane);
+        }
       }
     }
 #pragma unroll
@@ -349,9 +367,10 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
   nrm.init(stats_e, E > 0 ? 1.0 / (double)E : 0.0, gamma, beta, lane);
   const float* Gf = G;
   const float* Gb = G + N * 2 * D;
-  double s1[VPL], s2[VPL];
+  // gradient statistics (dbeta_e, dgamma_e): fp32 per thread over its few nodes, fp64 across the grid
+  float f1[VPL], f2[VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
+  for (int k = 0; k < VPL; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
   for (int64_t v = gw; v < N; v += nw) {
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> gnf, gdf, a3, acc;
@@ -361,38 +380,57 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
       gdf.load(Gf + v * (2 * D) + D, lane);
       a3.load(P + v * (5 * D) + 2 * D, lane);
     }
+    auto edge_math = [&](Row<D>& x, const Row<D>& ein, Row<D>& ge, const Row<D>& gnb, const Row<D>& gdb,
+                         const Row<D>& a2) {
+      nrm.normalize(x);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const float nv = x.v[k] * nrm.gamma[k] + nrm.beta[k];
+        const float eo = fmaxf(nv, 0.f) + (residual ? ein.v[k] : 0.f);
+        const float sg = sigmoidf_(eo);
+        const float gs = gnf.v[k] * a2.v[k] + gdf.v[k] + gnb.v[k] * a3.v[k] + gdb.v[k];
+        const float geo = ge.v[k] + gs * sg * (1.0f - sg);
+        ge.v[k] = geo;
+        const float gn = nv > 0.f ? geo : 0.f;
+        f1[k] += gn;
+        f2[k] = fmaf(gn, x.v[k], f2[k]);
+        acc.v[k] = fmaf(sg, gnb.v[k], acc.v[k]);
+      }
+    };
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
       const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
-      for (int j = 0; j < cnt; ++j) {
-        const int64_t i = base + j;
-        const int64_t s = __shfl_sync(0xffffffffu, my_s, j);
-        Row<D> x, ein, ge, gnb, gdb, a2;
-        x.load_stream(t + i * D, lane);
-        ein.load_stream(e_in + i * D, lane);
-        if (g_e) ge.load_stream(g_e + i * D, lane); else ge.fill(0.f);
-        gnb.load(Gb + s * (2 * D), lane);
-        gdb.load(Gb + s * (2 * D) + D, lane);
-        a2.load(P + s * (5 * D) + D, lane);
-        nrm.normalize(x);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const float nv = x.v[k] * nrm.gamma[k] + nrm.beta[k];
-          const float eo = fmaxf(nv, 0.f) + (residual ? ein.v[k] : 0.f);
-          const float sg = sigmoidf_(eo);
-          const float gs = gnf.v[k] * a2.v[k] + gdf.v[k] + gnb.v[k] * a3.v[k] + gdb.v[k];
-          const float geo = ge.v[k] + gs * sg * (1.0f - sg);
-          ge.v[k] = geo;
-          const float gn = nv > 0.f ? geo : 0.f;
-          s1[k] += (double)gn;
-          s2[k] += (double)gn * (double)x.v[k];
-          acc.v[k] = fmaf(sg, gnb.v[k], acc.v[k]);
+      for (int j = 0; j < cnt; j += 2) {
+        const bool two = (j + 1) < cnt;
+        const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
+        const int64_t sa = __shfl_sync(0xffffffffu, my_s, j);
+        const int64_t sb = __shfl_sync(0xffffffffu, my_s, two ? j + 1 : j);
+        Row<D> x0, ein0, ge0, gnb0, gdb0, a20, x1, ein1, ge1, gnb1, gdb1, a21;
+        x0.load_stream(t + i0 * D, lane);
+        ein0.load_stream(e_in + i0 * D, lane);
+        if (g_e) ge0.load_stream(g_e + i0 * D, lane); else ge0.fill(0.f);
+        gnb0.load(Gb + sa * (2 * D), lane);
+        gdb0.load(Gb + sa * (2 * D) + D, lane);
+        a20.load(P + sa * (5 * D) + D, lane);
+        x1.load_stream(t + i1 * D, lane);
+        ein1.load_stream(e_in + i1 * D, lane);
+        if (g_e) ge1.load_stream(g_e + i1 * D, lane); else ge1.fill(0.f);
+        gnb1.load(Gb + sb * (2 * D), lane);
+        gdb1.load(Gb + sb * (2 * D) + D, lane);
+        a21.load(P + sb * (5 * D) + D, lane);
+        edge_math(x0, ein0, ge0, gnb0, gdb0, a20);
+        ge0.store(g_eo + i0 * D, lane);
+        if (two) {
+          edge_math(x1, ein1, ge1, gnb1, gdb1, a21);
+          ge1.store(g_eo + i1 * D, lane);
         }
-        ge.store(g_eo + i * D, lane);
       }
     }
     acc.store(gP + v * (5 * D) + 2 * D, lane);
   }
+  double s1[VPL], s2[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) { s1[k] = (double)f1[k]; s2[k] = (double)f2[k]; }
   block_flush_stats<D>(s1, s2, bstats_e, bstats_e + D);
 }
 
@@ -422,20 +460,31 @@ edge_bwd_b_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> acc;
     acc.fill(0.f);
-    for (int64_t i = beg; i < end; ++i) {
-      Row<D> x, g;
-      x.load_stream(t + i * D, lane);
-      g.load_stream(g_eo + i * D, lane);
-      const float rr = nrm.normalize(x);
+    for (int64_t i = beg; i < end; i += 2) {
+      const bool two = (i + 1) < end;
+      const int64_t i1 = two ? i + 1 : i;
+      Row<D> x0, g0, x1, g1;
+      x0.load_stream(t + i * D, lane);
+      g0.load_stream(g_eo + i * D, lane);
+      x1.load_stream(t + i1 * D, lane);
+      g1.load_stream(g_eo + i1 * D, lane);
+      const float r0 = nrm.normalize(x0);
+      const float r1 = nrm.normalize(x1);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const float nv = x.v[k] * nrm.gamma[k] + nrm.beta[k];
-        g.v[k] = nv > 0.f ? g.v[k] : 0.f;
+        g0.v[k] = (x0.v[k] * nrm.gamma[k] + nrm.beta[k]) > 0.f ? g0.v[k] : 0.f;
+        g1.v[k] = (x1.v[k] * nrm.gamma[k] + nrm.beta[k]) > 0.f ? g1.v[k] : 0.f;
       }
-      nrm.backward(g, x, rr, m1, m2);
-      g.store(g_t + i * D, lane);
+      nrm.backward(g0, x0, r0, m1, m2);
+      g0.store(g_t + i * D, lane);
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) acc.v[k] += g.v[k];
+      for (int k = 0; k < VPL; ++k) acc.v[k] += g0.v[k];
+      if (two) {
+        nrm.backward(g1, x1, r1, m1, m2);
+        g1.store(g_t + i1 * D, lane);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc.v[k] += g1.v[k];
+      }
     }
     acc.store(gP + v * (5 * D) + 4 * D, lane);
   }

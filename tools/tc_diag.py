@@ -31,7 +31,7 @@ for (M, N, K) in [(128, 128, 32), (128, 128, 128), (1000, 128, 128), (372650, 12
     b = torch.randn(N, device=dev)
     g = torch.randn(M, N, device=dev)
     out = {}
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         _lib.set_tc_mode(mode)
         y = torch.empty(M, N, device=dev)
         f1 = lambda: check(lib.gg_linear_fwd(M, N, K, ptr(x), ptr(W), ptr(b), 0, ptr(y), st()), "fwd")
@@ -47,7 +47,7 @@ for (M, N, K) in [(128, 128, 32), (128, 128, 128), (1000, 128, 128), (372650, 12
     gx64 = g.double() @ W.double()
     dW64 = g.double().t() @ x.double()
     db64 = g.double().sum(0)
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         y, gx, dW, db, t1, t2, t3 = out[mode]
-        print(f"M={M} N={N} K={K} mode={'tc ' if mode else 'ffma'}: NT err {rel(y, y64):.2e} {t1:8.1f}us | "
+        print(f"M={M} N={N} K={K} mode={['ffma','tc  ','tcraw'][mode]}: NT err {rel(y, y64):.2e} {t1:8.1f}us | "
               f"NN err {rel(gx, gx64):.2e} {t2:8.1f}us | TN err {rel(dW, dW64):.2e} db {rel(db, db64):.2e} {t3:8.1f}us", flush=True)
