@@ -29,7 +29,7 @@ static unsigned node_grid(int64_t n) {
 
 // 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
 static int g_tc_mode = 1;
-namespace tc { int& tc_raw_hi_ref() { static int v = 1; return v; } }
+namespace tc { int& tc_dbg_ref() { static int v = 0; return v; } }
 
 static int pick_splits(int64_t K, int64_t tiles) {
   int64_t want = (2LL * sm_count() + tiles - 1) / tiles;
@@ -54,16 +54,25 @@ static int linear_fwd(const char* tag, int64_t M, int N, int K, const float* X, 
 }
 
 // dX[M,K] = dY[M,N] W[N,K] (+addend)(mask)
-static int linear_bwd_data(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W, int64_t ldw,
-                           const float* addend, const float* mask, float* dX, int64_t lddx, cudaStream_t st) {
+template <bool kAdd, bool kMask>
+static int linear_bwd_data_t(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W,
+                             int64_t ldw, const float* addend, const float* mask, float* dX, int64_t lddx,
+                             cudaStream_t st) {
   GemmArgs g{};
   g.A = dY; g.lda = lddy; g.B = W; g.ldb = ldw; g.M = M; g.N = K; g.K = N;
-  EpiAddMask epi{dX, lddx, addend, mask};
+  EpiAddMaskT<kAdd, kMask> epi{dX, lddx, addend, mask};
   if (g_tc_mode && tc::eligible(false, true, M, K, N, lddy, ldw, dY, W))
     return tc::launch<false, true, false, false>(tag, dY, lddy, W, ldw, M, K, N, 1, nullptr, nullptr, epi, sm_count(), st);
   if (K >= 128) return launch_gemm<128, false, false, false, false>(tag, g, epi, 1, st);
   if (K > 32) return launch_gemm<64, false, false, false, false>(tag, g, epi, 1, st);
   return launch_gemm<32, false, false, false, false>(tag, g, epi, 1, st);
+}
+static int linear_bwd_data(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* W,
+                           int64_t ldw, const float* addend, const float* mask, float* dX, int64_t lddx, cudaStream_t st) {
+  if (addend && mask) return linear_bwd_data_t<true, true>(tag, M, N, K, dY, lddy, W, ldw, addend, mask, dX, lddx, st);
+  if (addend) return linear_bwd_data_t<true, false>(tag, M, N, K, dY, lddy, W, ldw, addend, mask, dX, lddx, st);
+  if (mask) return linear_bwd_data_t<false, true>(tag, M, N, K, dY, lddy, W, ldw, addend, mask, dX, lddx, st);
+  return linear_bwd_data_t<false, false>(tag, M, N, K, dY, lddy, W, ldw, addend, mask, dX, lddx, st);
 }
 
 // dW[N,K] = dY[M,N]^T X[M,K] ; db[N] = colsum(dY)       (dW, db zeroed here)
@@ -257,12 +266,11 @@ using namespace gg;
 
 extern "C" {
 
+int gg_debug_flags(int flags) { const int old = tc::tc_dbg_ref(); tc::tc_dbg_ref() = flags; return old; }
+
 int gg_set_tc_mode(int mode) {
-  const int old = g_tc_mode ? (tc::tc_raw_hi_ref() ? 2 : 1) : 0;
+  const int old = g_tc_mode;
   g_tc_mode = mode ? 1 : 0;
-  // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (measured: identical results with and
-  // without rewriting hi in place), so by default the TMA-landed tile is the hi operand; 2 forces the rewrite
-  tc::tc_raw_hi_ref() = (mode == 2) ? 0 : 1;
   return old;
 }
 

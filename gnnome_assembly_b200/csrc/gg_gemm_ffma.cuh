@@ -13,6 +13,8 @@
 // is called by ALL threads uniformly (so it may use warp shuffles among the 16 lanes that share a row);
 // it must write its own outputs when `valid`, and leave the final values in acc[] (used for column stats).
 #pragma once
+#include <type_traits>
+
 #include "gg_common.cuh"
 
 namespace gg {
@@ -238,14 +240,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_ffma_kernel(GemmArgs g, 
 
 // ------------------------------------------------------------------------------------ epilogues
 // Y = acc + bias (optional) ; optional ReLU ; store
-// (tensor-core kernel: `Pre` holds the epilogue's global operands for one float4 of output, fetched by
-//  prefetch() a chunk ahead; apply_pre() finishes the element; kIdx = needs the row's src/dst node ids)
+// (tensor-core kernel: PreD / PreN hold the epilogue's global operands for one float4 of output, fetched a
+//  whole tile ahead (deep: random gathers, streams) or one chunk ahead (near: cache-friendly operands);
+//  apply_pre() finishes the element; kIdx = the functor needs the row's src/dst node ids)
 struct EpiBias {
   float* C; int64_t ldc; const float* bias; int relu;
   static constexpr bool kIdx = false;
-  struct Pre {};
-  __device__ __forceinline__ void prefetch(Pre&, int64_t, int, int, int) const {}
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre&, bool valid) const {
+  struct PreD {};
+  struct PreN {};
+  __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void prefetch_near(PreN&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, bool valid) const {
     apply<4>(m, n, acc, valid);
   }
   template <int GW>
@@ -262,34 +267,43 @@ struct EpiBias {
 };
 
 // dX = acc (+ addend) ; zero where mask <= 0 ; store          (bwd-data, ReLU backward fused)
-struct EpiAddMask {
+// kAdd / kMask select at compile time which operands exist (so the tensor-core epilogue only holds prefetch
+// registers for what it uses)
+template <bool kAdd, bool kMask>
+struct EpiAddMaskT {
   float* C; int64_t ldc; const float* addend; const float* mask;
-  static constexpr bool kIdx = false;
-  struct Pre { float4 add, msk; };
-  __device__ __forceinline__ void prefetch(Pre& p, int64_t m, int n, int, int) const {
-    p.add = addend ? __ldg(reinterpret_cast<const float4*>(addend + m * ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    p.msk = mask ? __ldg(reinterpret_cast<const float4*>(mask + m * ldc + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
-  }
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre& p, bool valid) const {
-    if (!valid) return;
-    acc[0] = p.msk.x > 0.f ? acc[0] + p.add.x : 0.f;
-    acc[1] = p.msk.y > 0.f ? acc[1] + p.add.y : 0.f;
-    acc[2] = p.msk.z > 0.f ? acc[2] + p.add.z : 0.f;
-    acc[3] = p.msk.w > 0.f ? acc[3] + p.add.w : 0.f;
-    *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
     if (!valid) return;
 #pragma unroll
     for (int j = 0; j < GW; ++j) {
       float v = acc[j];
-      if (addend) v += __ldg(addend + m * ldc + n + j);
-      if (mask && !(__ldg(mask + m * ldc + n + j) > 0.f)) v = 0.f;
+      if constexpr (kAdd) v += __ldg(addend + m * ldc + n + j);
+      if constexpr (kMask) { if (!(__ldg(mask + m * ldc + n + j) > 0.f)) v = 0.f; }
       acc[j] = v;
     }
     if constexpr (GW == 4) *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     else *reinterpret_cast<float2*>(C + m * ldc + n) = make_float2(acc[0], acc[1]);
+  }
+  static constexpr bool kIdx = false;
+  struct Empty {};
+  struct Val { float4 v; };
+  using PreD = typename std::conditional<kAdd, Val, Empty>::type;
+  using PreN = typename std::conditional<kMask, Val, Empty>::type;
+  __device__ __forceinline__ void prefetch_deep(PreD& p, int64_t m, int n, int, int) const {
+    if constexpr (kAdd) p.v = __ldg(reinterpret_cast<const float4*>(addend + m * ldc + n));
+  }
+  __device__ __forceinline__ void prefetch_near(PreN& p, int64_t m, int n, int, int) const {
+    if constexpr (kMask) p.v = __ldg(reinterpret_cast<const float4*>(mask + m * ldc + n));
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, bool valid) const {
+    if (!valid) return;
+    if constexpr (kAdd) { acc[0] += d.v.x; acc[1] += d.v.y; acc[2] += d.v.z; acc[3] += d.v.w; }
+    if constexpr (kMask) {
+      acc[0] = p.v.x > 0.f ? acc[0] : 0.f; acc[1] = p.v.y > 0.f ? acc[1] : 0.f;
+      acc[2] = p.v.z > 0.f ? acc[2] : 0.f; acc[3] = p.v.w > 0.f ? acc[3] : 0.f;
+    }
+    *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 };
 
@@ -297,9 +311,11 @@ struct EpiAddMask {
 struct EpiAtomic {
   float* C; int64_t ldc;
   static constexpr bool kIdx = false;
-  struct Pre {};
-  __device__ __forceinline__ void prefetch(Pre&, int64_t, int, int, int) const {}
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre&, bool valid) const {
+  struct PreD {};
+  struct PreN {};
+  __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void prefetch_near(PreN&, int64_t, int, int, int) const {}
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, bool valid) const {
     apply<4>(m, n, acc, valid);
   }
   template <int GW>
@@ -315,18 +331,21 @@ struct EpiAtomic {
 struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
-  struct Pre { float4 p1, p2; };
-  __device__ __forceinline__ void prefetch(Pre& p, int64_t, int n, int s, int v) const {
+  struct PreD { float4 p1; };     // B1h[src]: random row gather -> a whole tile ahead
+  struct PreN { float4 p2; };     // B2h[dst]: edges are dst-sorted, consecutive rows share it -> one chunk ahead
+  __device__ __forceinline__ void prefetch_deep(PreD& p, int64_t, int n, int s, int) const {
     p.p1 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)s * (5 * d) + 3 * d + n));
+  }
+  __device__ __forceinline__ void prefetch_near(PreN& p, int64_t, int n, int, int v) const {
     p.p2 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)v * (5 * d) + 4 * d + n));
   }
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const Pre& p, bool valid) const {
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& dp, const PreN& np, bool valid) const {
     if (!valid) return;
     const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + n));
-    acc[0] = (p.p1.x + p.p2.x) + (acc[0] + b.x);
-    acc[1] = (p.p1.y + p.p2.y) + (acc[1] + b.y);
-    acc[2] = (p.p1.z + p.p2.z) + (acc[2] + b.z);
-    acc[3] = (p.p1.w + p.p2.w) + (acc[3] + b.w);
+    acc[0] = (dp.p1.x + np.p2.x) + (acc[0] + b.x);
+    acc[1] = (dp.p1.y + np.p2.y) + (acc[1] + b.y);
+    acc[2] = (dp.p1.z + np.p2.z) + (acc[2] + b.z);
+    acc[3] = (dp.p1.w + np.p2.w) + (acc[3] + b.w);
     *reinterpret_cast<float4*>(t + m * d + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
   template <int GW>

@@ -1,24 +1,29 @@
-// gg_gemm_tc.cuh — 3xTF32 GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulators in
-// TMEM, operands staged by TMA with 128-byte swizzle), with the same pluggable epilogues as the FFMA GEMM.
+// gg_gemm_tc.cuh — 3xTF32 GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulators AND the
+// A operand in TMEM, B operand and raw A tiles staged by TMA with 128-byte swizzle), with the same pluggable
+// epilogues as the FFMA GEMM.
 //
 // Why 3xTF32: the reference runs its projections in true fp32 (torch allow_tf32=False,
 // layers/gated_gcn_full.py:44,107-113) and plain TF32 misses the 1e-4 logit tolerance.
-// Each fp32 operand x is split as x = hi + lo with hi = x with the low 13 mantissa bits cleared (exactly a
-// TF32 number) and lo = x - hi (exact in fp32); D = A_hi B_hi + A_lo B_hi + A_hi B_lo drops only the
-// lo*lo term (~2^-20 relative).  TMA lands the raw fp32 tile; four "splitter" warps rewrite it in place
-// as hi and write lo to a second buffer with the same (swizzled) byte layout, so the split is layout
-// agnostic; one thread issues the 3 MMAs per K step.
+// Each fp32 operand x is split as x = hi + lo, hi = x with the low 13 mantissa bits dropped (what kind::tf32
+// reads anyway), lo = x - hi (exact in fp32); D = A_lo B_hi + A_hi B_lo + A_hi B_hi drops only lo*lo (~2^-20).
 //
-// Tile: 128 (M) x 128 (N) x 32 (K, = one 128-byte swizzle row of fp32), 3-stage mbarrier pipeline,
-// persistent CTAs (one per SM), two TMEM accumulators (2 x 128 columns) so the epilogue of tile i
-// overlaps the main loop of tile i+1.
-//   warp 0      TMA producer          warp 1   MMA issuer        warp 2   TMEM allocator
-//   warps 4-7   hi/lo splitter        warps 8-15  epilogue, two groups of 4 warps, 64 columns each
-//                                     (TMEM -> registers -> smem -> coalesced row segments, operands of the
-//                                      fused epilogue prefetched one chunk ahead)
-// Operand layouts (template flags): K-major = the reduction index is contiguous in global memory
-// (A[M,K] row-major, nn.Linear W[N,K]); MN-major = the M / N index is contiguous (B[K,N] in bwd-data,
-// both operands in weight gradients).  Descriptor encodings follow CUTLASS cute/arch/mma_sm100_desc.hpp.
+// Data flow per 128 x 128 x 32 K-block (32 fp32 = one 128-byte swizzle row), 4-stage mbarrier ring:
+//   TMA      : raw A tile (16 KB) and raw B tile (16 KB) -> shared memory
+//   converter: 4 warps, thread = A row: row -> registers -> (hi, lo) -> TMEM via tcgen05.st  (A never goes
+//              back to shared memory; the MMA reads it from TMEM, "TS" form) ; B_lo = B - trunc(B) is written
+//              next to B (same swizzled byte layout, so the split is layout agnostic)
+//   MMA      : one thread, 3 x 4 tcgen05.mma per K-block, fp32 accumulators in TMEM (2 x 128 columns, so the
+//              epilogue of tile i overlaps the main loop of tile i+1)
+//   epilogue : 8 warps in two groups of 64 columns: TMEM -> registers -> shared staging -> row-wise coalesced
+//              global traffic; the fused epilogue's gathered operands are prefetched into registers a whole
+//              tile ahead ("deep") / one 16-column chunk ahead ("near"), register budget via setmaxnreg.
+// Shared-memory traffic per K-block: 32 KB TMA + 16 KB (A read) + 32 KB (B split) + 48 KB (MMA reads B) —
+// the SS form (A_hi/A_lo in shared memory) needed 192 KB and was bound by shared-memory bandwidth
+// (profiles/r1_ncu_full_fwd_kernels_tc_ss.txt: l1tex 62-73 %, tensor pipe 16-30 %).
+// Persistent CTAs, one per SM.  Operand layouts (template flags): K-major = reduction index contiguous in
+// global memory (A[M,K] row-major, nn.Linear W[N,K]); MN-major = the M / N index contiguous (B[K,N] in
+// bwd-data, both operands in weight gradients).  Descriptor encodings follow CUTLASS
+// cute/arch/mma_sm100_desc.hpp.
 #pragma once
 #include <cuda.h>
 
@@ -28,21 +33,21 @@
 namespace gg {
 namespace tc {
 
-int& tc_raw_hi_ref();
-inline int tc_raw_hi() { return tc_raw_hi_ref(); }
-
 constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo
 constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
 constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
 constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
-constexpr int BIAS_BYTES = 2 * 2 * BM * 4;        // per epilogue group: src / dst node id of the tile's 128 rows
+constexpr int IDX_BYTES = 2 * 2 * 2 * BM * 4;     // per epilogue group, double buffered: src / dst node ids of 128 rows
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + BAR_BYTES;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + IDX_BYTES + BAR_BYTES;
 constexpr int THREADS = 512;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                    // 2 x 128 accumulator columns + 4 stages x (32 hi + 32 lo) A columns
+constexpr int TMEM_A0 = 256;
+
+int& tc_dbg_ref();                                // experiment switches, see Args::dbg
 
 struct Args {
   int64_t M; int N; int64_t K;
@@ -50,7 +55,7 @@ struct Args {
   int64_t k_chunk;           // multiple of BK
   double* col_stats;         // kStats: [2N]
   float* bias_grad;          // kBiasGrad (A MN-major only): [M] sums of A over k
-  int raw_hi;                // 1: leave the TMA-landed fp32 tile as the hi operand (tensor core drops the low bits)
+  int dbg;                   // experiment switches (tools/epi_experiment.py): 1 = skip column stats, 2 = skip epilogue prefetches
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -89,6 +94,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from TMEM ("TS" form): lane = row, one tf32 per 32-bit column
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -158,22 +187,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
-  float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
-  double* sstat = reinterpret_cast<double*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES);
-  int* sidx = reinterpret_cast<int*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES);
-  const uint32_t bars = base + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + BIAS_BYTES + 128);
+  constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + STATS_BYTES,
+                OFF_BAR = OFF_IDX + IDX_BYTES;
+  float* staging = reinterpret_cast<float*>(gen + OFF_STG);
+  double* sstat = reinterpret_cast<double*>(gen + OFF_STAT);
+  int* sidx = reinterpret_cast<int*>(gen + OFF_IDX);
+  const uint32_t bars = base + OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BAR + 128);
   auto full_raw = [&](int s) { return bars + 8u * s; };
-  auto full_split = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tmem_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
   auto tmem_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
 
+  // register split (setmaxnreg): a fused epilogue that holds a whole tile of prefetched operands gets more
+  constexpr bool kHeavyEpi = (sizeof(typename Epi::PreD) + sizeof(typename Epi::PreN)) >= 32;
+  constexpr int kCtrlRegs = kHeavyEpi ? 24 : 40, kConvRegs = kHeavyEpi ? 96 : 104, kEpiRegs = kHeavyEpi ? 192 : 184;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_split(s), 128); mbar_init(empty(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), 128); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -203,9 +237,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     nkb = (int)((kend - kbeg + BK - 1) / BK);
   };
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
+  if (warp < 4) {
+    reg_dec<kCtrlRegs>();
+    if (warp == 0 && lane == 0) {
+      // ================================================================ TMA producer
       int s = 0; uint32_t ph = 0;
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
@@ -222,19 +257,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &tmA, full_raw(s), mt * BM + 32 * j, k0);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(st + 2 * TILE_BYTES, &tmB, full_raw(s), k0, nt * BN);
+            tma_load_2d(st + TILE_BYTES, &tmB, full_raw(s), k0, nt * BN);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(st + 2 * TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
+            for (int j = 0; j < 4; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+    } else if (warp == 1 && lane == 0) {
+      // ================================================================ MMA issuer (one thread)
+      constexpr uint32_t idesc = make_idesc(false, B_MN);          // A comes from TMEM: always K-major there
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
@@ -243,115 +276,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_split(s), ph);
+          mbar_wait(full_ab(s), ph);
           tc_fence_after();
           const uint32_t st = stage0 + s * STAGE_BYTES;
-          // K step (8 tf32): K-major = 32 B inside the swizzle row; MN-major = 8 k-rows = 1 KB
-          const uint64_t a_hi = make_desc<A_MN>(st);
-          const uint64_t a_lo = make_desc<A_MN>(st + TILE_BYTES);
-          const uint64_t b_hi = make_desc<B_MN>(st + 2 * TILE_BYTES);
-          const uint64_t b_lo = make_desc<B_MN>(st + 3 * TILE_BYTES);
-          constexpr uint64_t a_step = A_MN ? (1024 >> 4) : (32 >> 4);
-          constexpr uint64_t b_step = B_MN ? (1024 >> 4) : (32 >> 4);
+          const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A0 + 64 * s), a_lo = a_hi + 32;
+          const uint64_t b_hi = make_desc<B_MN>(st + TILE_BYTES);
+          const uint64_t b_lo = make_desc<B_MN>(st + 2 * TILE_BYTES);
+          constexpr uint64_t b_step = B_MN ? (1024 >> 4) : (32 >> 4);   // 8 tf32 along K: 8 k-rows / 32 bytes
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-            umma_tf32(d_tmem, a_lo + ks * a_step, b_hi + ks * b_step, idesc, first);   // small terms first
-            umma_tf32(d_tmem, a_hi + ks * a_step, b_lo + ks * b_step, idesc, 1u);
-            umma_tf32(d_tmem, a_hi + ks * a_step, b_hi + ks * b_step, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_lo + 8 * ks, b_hi + ks * b_step, idesc, first);   // small terms first
+            umma_tf32_ts(d_tmem, a_hi + 8 * ks, b_lo + ks * b_step, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + 8 * ks, b_hi + ks * b_step, idesc, 1u);
           }
-          umma_commit(empty(s));                       // frees the stage when these MMAs have read it
+          umma_commit(empty(s));                       // frees the stage (smem B, TMEM A) when these MMAs are done
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(tmem_full(acc));                   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================================================ hi/lo splitter (128 threads)
+  } else if (warp < 8) {
+    // ================================================================ converter (128 threads, thread = A row)
+    reg_dec<kConvRegs>();
     const int t = threadIdx.x - 128;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     int s = 0; uint32_t ph = 0;
-    float4 bsum[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, sp; decode(w, mt, nt, sp);
       int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+      float bsum = 0.f;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_raw(s), ph);
-        uint8_t* st = gen + s * STAGE_BYTES;
+        const uint8_t* st = gen + s * STAGE_BYTES;
+        // ---- A row t of this K-block -> registers (k order), hi = raw bits, lo = x - trunc(x)
+        uint32_t hi[32], lo[32];
+        if constexpr (!A_MN) {
+          // K-major SWIZZLE_128B tile: row t at t*128 B, logical 16-byte chunk c stored at chunk c ^ (t % 8)
+          const float4* row = reinterpret_cast<const float4*>(st + t * 128);
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {
-          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = row[c ^ (t & 7)];
+            hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
+            hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+          }
+        } else {
+          // MN-major 128B_ATOM_32B tile: box t/32 (4 KB), k-row k at k*128 B, m' = t%32 lives in 32-byte chunk
+          // (m'/8) ^ (k % 4) at word m' % 8  -> for a fixed k a warp reads one whole 128-byte row: conflict free
+          const uint8_t* box = st + (t >> 5) * 4096;
+          const int mp = t & 31;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            hi[k] = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((mp >> 3) ^ (k & 3)) << 5) | ((mp & 7) << 2)));
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = __uint_as_float(hi[k]);
+          lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
+          if constexpr (kBiasGrad) bsum += x;
+        }
+        const uint32_t ta = tmem_base + lane_base + (uint32_t)(TMEM_A0 + 64 * s);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        // ---- B_lo = B - trunc(B), element-wise at identical (swizzled) byte offsets
+        {
+          const float4* bh = reinterpret_cast<const float4*>(st + TILE_BYTES);
+          float4* bl = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + 2 * TILE_BYTES);
 #pragma unroll
           for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
             const int q = t + 128 * i;
-            const float4 x = hi[q];
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-            if (!g.raw_hi) hi[q] = h;
-            lo[q] = l;
-            if constexpr (kBiasGrad && A_MN) {
-              // A tile is [k][m] in 4 boxes of 32 m; float4 q lives in box q/256 (= i/2), its m chunk is fixed per thread
-              if (op == 0) { bsum[i >> 1].x += x.x; bsum[i >> 1].y += x.y; bsum[i >> 1].z += x.z; bsum[i >> 1].w += x.w; }
-            }
+            const float4 x = bh[q];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            bl[q] = l;
           }
         }
-        proxy_fence_async();                           // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full_split(s));
+        tmem_st_wait();
+        tc_fence_before();
+        proxy_fence_async();                           // generic-proxy smem writes -> visible to the tensor core
+        mbar_arrive(full_ab(s));
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      if constexpr (kBiasGrad && A_MN) {
-        if (g.bias_grad != nullptr && nt == 0) {
-          // 128B_ATOM_32B swizzle: physical 32-byte chunk j' = (t % 8) / 2 of k-row r (r % 4 = (t / 8) % 4)
-          // holds logical 32-byte chunk j' ^ (r % 4); the 16-byte half inside it is unchanged
-          const int c = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t m = (int64_t)mt * BM + 32 * j + 4 * c;
-            if (m < g.M) {
-              atomicAdd(g.bias_grad + m + 0, bsum[j].x); atomicAdd(g.bias_grad + m + 1, bsum[j].y);
-              atomicAdd(g.bias_grad + m + 2, bsum[j].z); atomicAdd(g.bias_grad + m + 3, bsum[j].w);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (kBiasGrad) {
+        const int64_t m = (int64_t)mt * BM + t;
+        if (g.bias_grad != nullptr && nt == 0 && m < g.M) atomicAdd(g.bias_grad + m, bsum);
       }
     }
-  } else if (warp >= 8) {
+  } else {
     // ================================================================ epilogue (2 groups x 128 threads)
     // group grp owns accumulator columns [64 grp, 64 grp + 64), 4 chunks of 16 columns.  Per chunk: every
     // thread pulls its row (TMEM lane) out of TMEM, parks it in the group's staging tile, then the group
     // walks the tile row-wise (4 threads x float4 = one 64-byte row segment) so that all global traffic of
-    // the fused epilogue is coalesced.  The epilogue's global operands for chunk q+1 are prefetched into
-    // registers before chunk q is processed (double buffer), the tile's src/dst ids one tile ahead.
+    // the fused epilogue is coalesced.
+    reg_inc<kEpiRegs>();
     const int grp = (warp - 8) >> 2;
     const int ew = warp & 3;                            // TMEM lanes 32*ew .. 32*ew+31
     const int tg = (threadIdx.x - 256) & 127;           // thread in group == accumulator row of the tile
     const uint32_t bar_id = 1 + grp;
     float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
-    int* s_src = sidx + grp * 2 * BM;
-    int* s_dst = s_src + BM;
+    int* idx_base = sidx + grp * 4 * BM;                // [2 buffers][src | dst][128]
     const int c4 = (tg & 3) * 4;                        // column offset of this thread inside a chunk
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
-    using Pre = typename Epi::Pre;
-    Pre pre[2][4];
+    using PreD = typename Epi::PreD;
+    using PreN = typename Epi::PreN;
+    // The fused epilogue's global operands (gathered projection rows / streamed addends) for the WHOLE next
+    // tile are fetched into registers in one batch right after the current tile has been processed, and
+    // nothing is fetched while a tile is being consumed: a warp has only six load scoreboards, so a load
+    // issued between two uses would make the older, already-landed operands wait for it.  The batch lands
+    // while this group waits for the next accumulator (the MMA main loop of a tile is longer than a DRAM trip).
+    PreD deep[4][4];                                    // [chunk][pass]
+    PreN near[4][4];
 
-    auto prefetch = [&](Pre (&dst)[4], int mt_, int nt_, int q) {
+    auto row_of = [&](int mt_, int p) {
+      int64_t m = (int64_t)mt_ * BM + p * 32 + (tg >> 2);
+      return m < g.M ? m : g.M - 1;
+    };
+    auto col_of = [&](int nt_, int q) { return nt_ * BN + 64 * grp + EC * q + c4; };
+    auto fetch_tile = [&](int mt_, int nt_, int buf) {
+      if (g.dbg & 2) return;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int r = p * 32 + (tg >> 2);
-        int64_t m = (int64_t)mt_ * BM + r;
-        if (m >= g.M) m = g.M - 1;
-        const int n = nt_ * BN + 64 * grp + EC * q + c4;
         int sv = 0, dv = 0;
-        if constexpr (Epi::kIdx) { sv = s_src[r]; dv = s_dst[r]; }
-        epi.prefetch(dst[p], m, n, sv, dv);
+        if constexpr (Epi::kIdx) { sv = idx_base[buf * 2 * BM + r]; dv = idx_base[buf * 2 * BM + BM + r]; }
+        const int64_t m = row_of(mt_, p);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          epi.prefetch_deep(deep[q][p], m, col_of(nt_, q), sv, dv);
+          epi.prefetch_near(near[q][p], m, col_of(nt_, q), sv, dv);
+        }
       }
     };
     auto load_idx = [&](int mt_, int& sv, int& dv) {
@@ -362,35 +419,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         dv = __ldg(epi.dst + m);
       }
     };
+    auto store_idx = [&](int buf, int sv, int dv) {
+      if constexpr (Epi::kIdx) { idx_base[buf * 2 * BM + tg] = sv; idx_base[buf * 2 * BM + BM + tg] = dv; }
+    };
 
     int acc = 0; uint32_t acc_ph = 0;
+    int cur = 0;                                        // idx buffer of the current tile
     int64_t w = blockIdx.x;
-    int mt = 0, nt = 0, sp = 0;
+    int mt = 0, nt = 0, sp = 0, mtn = 0, ntn = 0, spn = 0;
     if (w < total_work) {
       decode(w, mt, nt, sp);
       int sv = 0, dv = 0;
       load_idx(mt, sv, dv);
-      if constexpr (Epi::kIdx) { s_src[tg] = sv; s_dst[tg] = dv; }
+      store_idx(0, sv, dv);
+      if (w + gridDim.x < total_work) {
+        decode(w + gridDim.x, mtn, ntn, spn);
+        load_idx(mtn, sv, dv);
+        store_idx(1, sv, dv);
+      }
       group_bar();
-      prefetch(pre[0], mt, nt, 0);
+      fetch_tile(mt, nt, 0);
     }
     for (; w < total_work; w += gridDim.x) {
-      const int64_t wn = w + gridDim.x;
-      int mtn = 0, ntn = 0, spn = 0, nsv = 0, ndv = 0;
-      if (wn < total_work) { decode(wn, mtn, ntn, spn); load_idx(mtn, nsv, ndv); }
+      const int64_t wn = w + gridDim.x, wnn = wn + gridDim.x;
+      const bool has_next = wn < total_work;
       mbar_wait(tmem_full(acc), acc_ph);
       tc_fence_after();
       const int64_t m0 = (int64_t)mt * BM;
-      const int n0 = nt * BN + 64 * grp;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        // prefetch the operands of the next chunk (or of the next tile's first chunk)
-        if (q < 3) {
-          prefetch(pre[(q + 1) & 1], mt, nt, q + 1);
-        } else if (wn < total_work) {
-          if constexpr (Epi::kIdx) { s_src[tg] = nsv; s_dst[tg] = ndv; group_bar(); }
-          prefetch(pre[0], mtn, ntn, 0);
-        }
         float v[EC];
         tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q), v);
         if (q == 3) {                                   // accumulator fully read: hand it back to the MMA warp
@@ -401,25 +458,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 4; ++j)
           stg[tg * 4 + (j ^ ((tg >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         group_bar();
-        double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const int r = p * 32 + (tg >> 2);
           const float4 x = stg[r * 4 + ((tg & 3) ^ ((r >> 1) & 3))];
           float a[4] = {x.x, x.y, x.z, x.w};
           const int64_t m = m0 + r;
-          const int n = n0 + EC * q + c4;
+          const int n = col_of(nt, q);
           const bool valid = (m < g.M) && (n < g.N);
-          epi.apply_pre(m, n, a, pre[q & 1][p], valid);
+          epi.apply_pre(m, n, a, deep[q][p], near[q][p], valid);
           if constexpr (kStats) {
-            if (valid) {
+            if (valid && !(g.dbg & 1)) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { s1[j] += (double)a[j]; s2[j] += (double)a[j] * (double)a[j]; }
+              for (int j = 0; j < 4; ++j) { s1[j] += a[j]; s2[j] = fmaf(a[j], a[j], s2[j]); }
             }
           }
         }
-        if constexpr (kStats) {
-          // lanes l, l+4, ..., l+28 own the same 4 columns
+        if (kStats && !(g.dbg & 1)) {
+          // column statistics: fp32 over this chunk's 128 rows (4 per thread, then the 8 lanes l, l+4, ..,
+          // l+28 that own the same 4 columns), fp64 from there on
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -431,8 +489,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane < 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 0] += s1[j];
-              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 1] += s2[j];
+              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 0] += (double)s1[j];
+              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 1] += (double)s2[j];
             }
           }
         }
@@ -440,9 +498,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if constexpr (kStats) {
         // flush this tile's column statistics (the n tile can change between work items)
-        double a = 0.0, b = 0.0;
         const int col = 64 * grp + (tg & 63);
         if (tg < 64) {
+          double a = 0.0, b = 0.0;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) { a += sstat[(qq * BN + col) * 2]; b += sstat[(qq * BN + col) * 2 + 1]; }
 #pragma unroll
@@ -450,9 +508,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int n = nt * BN + col;
           if (n < g.N) { atomicAdd(g.col_stats + n, a); atomicAdd(g.col_stats + g.N + n, b); }
         }
-        group_bar();
       }
+      // one batch: every operand of the next tile, then the node ids of the tile after it
+      if (has_next) fetch_tile(mtn, ntn, cur ^ 1);
+      int mtt = 0, ntt = 0, spt = 0;
+      if (wnn < total_work) {
+        int nsv = 0, ndv = 0;
+        decode(wnn, mtt, ntt, spt);
+        load_idx(mtt, nsv, ndv);
+        store_idx(cur, nsv, ndv);                       // buffer of the tile just finished
+      }
+      group_bar();
       mt = mtn; nt = ntn; sp = spn;
+      mtn = mtt; ntn = ntt; spn = spt;
+      cur ^= 1;
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   }
@@ -533,7 +602,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   g.splits = (int)((K + chunk - 1) / chunk);
   g.col_stats = col_stats;
   g.bias_grad = bias_grad;
-  g.raw_hi = tc_raw_hi();
+  g.dbg = tc_dbg_ref();
   const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
   const int grid = (int)(work < num_sms ? work : num_sms);
   auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi>;
