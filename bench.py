@@ -270,15 +270,14 @@ def run_ours(args):
     sync_all()
 
     # per-kernel pass: CUDA event pair around every launch, on the launching stream (not the timed region)
-    prof = {}
-    if rank == 0:
-        _lib.profile(True)
-        for _ in range(3):
-            flush.zero_()
-            step(d_e, d_pe, d_y)
-        torch.cuda.synchronize()
-        _lib.profile(False)
-        prof = _lib.profile_report()
+    # (every rank runs these steps — they contain the gradient all-reduce — but only rank 0 records events)
+    _lib.profile(rank == 0)
+    for _ in range(3):
+        flush.zero_()
+        step(d_e, d_pe, d_y)
+    torch.cuda.synchronize()
+    _lib.profile(False)
+    prof = _lib.profile_report() if rank == 0 else {}
 
     # max over ranks, sum of edges
     t = torch.tensor([t_dev, t_e2e, float(E)], device=dev, dtype=torch.float64)
