@@ -41,6 +41,9 @@ const char* gg_last_error(void);
 /* gg_set_tc_mode(1) (default): projections with N % 128 == 0 run on the tcgen05 3xTF32 tensor-core kernel;
  * gg_set_tc_mode(0): true-fp32 FFMA kernel everywhere.  Returns the previous mode. */
 int gg_set_tc_mode(int mode);
+/* experiment switches for the tensor-core GEMM epilogue (tools/epi_experiment.py): bit 0 skips the column
+ * statistics, bit 1 skips the epilogue operand prefetch (WRONG RESULTS; timing experiments only). Returns old. */
+int gg_debug_flags(int flags);
 int64_t gg_launch_count(void);
 int gg_profile_enable(int on);
 int gg_profile_report(char* buf, size_t cap);
