@@ -207,7 +207,8 @@ def run_ours(args):
     E, N = g.num_edges, g.num_nodes
     torch.manual_seed(0)
     model = gg.GraphGatedGCNModel(1, 2, D, HID_E, L, HID_S, True, NB_PE).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    use_graph = (world == 1) and not args.no_cuda_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
     bucket = GradBucket(model.parameters()) if world > 1 else None
     graph = gg.AssemblyGraph(torch.from_numpy(g.src), torch.from_numpy(g.dst), N)
     gg.plan_for(graph, dev)                                    # plan creation excluded from timing (once per graph)
@@ -226,6 +227,14 @@ def run_ours(args):
         opt.step()
         return loss
 
+    graphed = None
+    launches_per_step = None
+    if use_graph:
+        from gnnome_assembly_b200.train_step import GraphedTrainStep
+        n_before = _lib.launch_count()
+        graphed = GraphedTrainStep(model, opt, graph, d_e, d_pe, d_y, lambda s_, y_: bce_loss(s_, y_, POS_WEIGHT))
+        launches_per_step = (_lib.launch_count() - n_before) // 4      # 3 warm-up steps + 1 captured step
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -238,12 +247,16 @@ def run_ours(args):
             flush.zero_()                                      # L2 flush between steps, outside the event pair
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if host_inputs:
+            if host_inputs and graphed is not None:
+                graphed(h_e, h_pe, h_y).item()                 # H2D into the static buffers, replay, D2H of the loss
+            elif host_inputs:
                 e = h_e.to(dev, non_blocking=True)
                 pe = h_pe.to(dev, non_blocking=True)
                 y = h_y.to(dev, non_blocking=True)
                 loss = step(e, pe, y)
                 loss.item()                                    # D2H of the step's result (train.py:259)
+            elif graphed is not None:
+                graphed()
             else:
                 step(d_e, d_pe, d_y)
             b.record()
@@ -252,7 +265,7 @@ def run_ours(args):
         return sum(a.elapsed_time(b) for a, b in evs) / 1e3    # seconds
 
     for _ in range(max(args.warmup, 3)):
-        step(d_e, d_pe, d_y)
+        graphed() if graphed is not None else step(d_e, d_pe, d_y)
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = _lib.launch_count()
@@ -260,7 +273,7 @@ def run_ours(args):
     t_dev = timed(args.steps, host_inputs=False)
     sync_all()
     t_wall1 = time.perf_counter()
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() - n0 if graphed is None else launches_per_step * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # e2e: same step from pinned host buffers, loss read back every step
@@ -325,6 +338,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 8-layer GatedGCN d=128 (BatchNorm) fwd+bwd+Adam on one chr19-like "
                    "synthetic assembly graph per GPU", "layers": L, "hidden": D, "nodes": N, "edges": E,
                    "parallelism": f"dp{world} (independent graphs, NCCL grad all-reduce)" if world > 1 else "single GPU",
+                   "cuda_graph": bool(use_graph),
                    "l2": "512 MB memset between timed steps (outside the per-step event pairs); per-step working "
                    "set ~5 GB >> 126 MB L2"},
         "edge_layers_per_s": value * L,
@@ -353,6 +367,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (default: the step "
+                    "is captured once into a CUDA graph and replayed)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -201,17 +201,27 @@ node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
       const int cnt = min(32, end - base);
       const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
       const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
-      for (int j = 0; j < cnt; ++j) {
-        const int64_t i = __shfl_sync(0xffffffffu, my_i, j);
-        const int64_t v = __shfl_sync(0xffffffffu, my_v, j);
-        Row<D> eo, a3;
-        eo.load(e_out + i * D, lane);
-        a3.load(P + v * (5 * D) + 2 * D, lane);
+      for (int j = 0; j < cnt; j += 4) {
+        // four out-edges in flight: all row gathers are issued before any math
+        Row<D> eo[4], a3[4];
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const float sg = sigmoidf_(eo.v[k]);
-          num.v[k] = fmaf(sg, a3.v[k], num.v[k]);
-          den.v[k] += sg;
+        for (int q = 0; q < 4; ++q) {
+          const int jj = (j + q < cnt) ? j + q : j;
+          const int64_t i = __shfl_sync(0xffffffffu, my_i, jj);
+          const int64_t v = __shfl_sync(0xffffffffu, my_v, jj);
+          eo[q].load(e_out + i * D, lane);
+          a3[q].load(P + v * (5 * D) + 2 * D, lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j + q < cnt) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              const float sg = sigmoidf_(eo[q].v[k]);
+              num.v[k] = fmaf(sg, a3[q].v[k], num.v[k]);
+              den.v[k] += sg;
+            }
+          }
         }
       }
     }
@@ -510,17 +520,26 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
       const int cnt = min(32, end - base);
       const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
       const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
-      for (int j = 0; j < cnt; ++j) {
-        const int64_t i = __shfl_sync(0xffffffffu, my_i, j);
-        const int64_t v = __shfl_sync(0xffffffffu, my_v, j);
-        Row<D> gt, eo, gnf;
-        gt.load(g_t + i * D, lane);
-        eo.load(e_out + i * D, lane);
-        gnf.load(Gf + v * (2 * D), lane);
+      for (int j = 0; j < cnt; j += 4) {
+        Row<D> gt[4], eo[4], gnf[4];
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          acc1.v[k] += gt.v[k];
-          acc2.v[k] = fmaf(sigmoidf_(eo.v[k]), gnf.v[k], acc2.v[k]);
+        for (int q = 0; q < 4; ++q) {
+          const int jj = (j + q < cnt) ? j + q : j;
+          const int64_t i = __shfl_sync(0xffffffffu, my_i, jj);
+          const int64_t v = __shfl_sync(0xffffffffu, my_v, jj);
+          gt[q].load(g_t + i * D, lane);
+          eo[q].load(e_out + i * D, lane);
+          gnf[q].load(Gf + v * (2 * D), lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j + q < cnt) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              acc1.v[k] += gt[q].v[k];
+              acc2.v[k] = fmaf(sigmoidf_(eo[q].v[k]), gnf[q].v[k], acc2.v[k]);
+            }
+          }
         }
       }
     }
