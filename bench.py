@@ -189,7 +189,6 @@ def run_ours(args):
     import gnnome_assembly_b200 as gg
     from gnnome_assembly_b200 import _lib
     from gnnome_assembly_b200.dp import GradBucket
-    from oracle.gatedgcn_oracle import bce_loss          # loss = train.py:211; plain torch op on the logits
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,6 +209,12 @@ def run_ours(args):
     use_graph = (world == 1) and not args.no_cuda_graph
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
     bucket = GradBucket(model.parameters()) if world > 1 else None
+    # train.py:210-211: criterion = BCEWithLogitsLoss(pos_weight=tensor([1 / pos_to_neg_ratio], device=device))
+    criterion = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([POS_WEIGHT], device=dev))
+
+    def bce_loss(scores, y, _pw=None):
+        return criterion(scores.squeeze(-1), y)
+
     graph = gg.AssemblyGraph(torch.from_numpy(g.src), torch.from_numpy(g.dst), N)
     gg.plan_for(graph, dev)                                    # plan creation excluded from timing (once per graph)
     # pinned host copies (the e2e arm) and device-resident copies (the kernel arm)
