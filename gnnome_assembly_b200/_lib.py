@@ -25,6 +25,7 @@ SIGNATURES = {
     "gg_profile_enable": (_i, [_i]),
     "gg_profile_report": (_i, [C.c_char_p, C.c_size_t]),
     "gg_plan_create": (_i, [_p, _p, _i64, _i64, _p, C.POINTER(_p)]),
+    "gg_plan_create_ex": (_i, [_p, _p, _i64, _i64, _i, _p, C.POINTER(_p)]),
     "gg_plan_destroy": (_i, [_p]),
     "gg_plan_num_nodes": (_i64, [_p]),
     "gg_plan_num_edges": (_i64, [_p]),

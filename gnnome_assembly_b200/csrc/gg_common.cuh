@@ -50,6 +50,8 @@ struct Plan {
   int32_t* out_dst = nullptr;  // [E] dst of that edge (saves one indirection)
   int32_t* perm = nullptr;     // [E] internal position -> caller edge id
   int32_t* inv_perm = nullptr; // [E]
+  int32_t* node_perm = nullptr; // [N] internal node id -> caller node id
+  int32_t* node_inv = nullptr;  // [N] caller node id -> internal node id
   int num_sms = 148;
 };
 

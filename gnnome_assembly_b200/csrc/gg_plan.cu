@@ -2,6 +2,7 @@
 // Replaces the structural role of the DGLGraph argument and of dgl.reverse
 // (models/full_graph.py:22, layers/gated_gcn_full.py:115): dgl.reverse keeps edge ids and swaps
 // src/dst, which here is simply "walk the out-edge CSR instead of the in-edge CSR".
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -66,6 +67,7 @@ static void free_plan(Plan* p) {
   if (!p) return;
   cudaFree(p->src); cudaFree(p->dst); cudaFree(p->in_ptr); cudaFree(p->out_ptr);
   cudaFree(p->out_eid); cudaFree(p->out_dst); cudaFree(p->perm); cudaFree(p->inv_perm);
+  cudaFree(p->node_perm); cudaFree(p->node_inv);
   delete p;
 }
 
@@ -118,6 +120,11 @@ int gg_profile_report(char* buf, size_t cap) {
 }
 
 int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t N, int64_t E, void* stream_, gg_plan_t** out) {
+  return gg_plan_create_ex(src, dst, N, E, GG_PLAN_RELABEL, stream_, out);
+}
+
+int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t E, int flags, void* stream_,
+                      gg_plan_t** out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GG_REQUIRE(out != nullptr, "plan_create: out is null");
   *out = nullptr;
@@ -137,6 +144,47 @@ int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
   }
   for (int64_t i = 0; i < E; ++i)
     GG_REQUIRE(hs[i] >= 0 && hs[i] < N && hd[i] >= 0 && hd[i] < N, "plan_create: node index out of range");
+
+  // ---- internal node order.  Assembly graphs are near-linear (an edge joins reads that overlap on the
+  // genome) but read ids are arbitrary, so row gathers of node features are random 512-byte DRAM accesses.
+  // A breadth-first (Cuthill-McKee style) relabelling over the undirected graph makes neighbours close in
+  // memory; legal because the model boundary exposes per-edge logits only.
+  std::vector<int32_t> node_perm((size_t)N), node_inv((size_t)N);      // internal -> caller, caller -> internal
+  if ((flags & GG_PLAN_RELABEL) && N > 0) {
+    std::vector<int32_t> uptr((size_t)N + 1, 0);
+    for (int64_t i = 0; i < E; ++i) { uptr[hs[i] + 1]++; uptr[hd[i] + 1]++; }
+    for (int64_t v = 0; v < N; ++v) uptr[v + 1] += uptr[v];
+    std::vector<int32_t> uadj((size_t)2 * E);
+    {
+      std::vector<int32_t> cur(uptr.begin(), uptr.end() - 1);
+      for (int64_t i = 0; i < E; ++i) { uadj[cur[hs[i]]++] = hd[i]; uadj[cur[hd[i]]++] = hs[i]; }
+    }
+    std::vector<int32_t> order((size_t)N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return (uptr[a + 1] - uptr[a]) < (uptr[b + 1] - uptr[b]);       // component seeds: lowest degree first
+    });
+    std::vector<char> seen((size_t)N, 0);
+    int64_t filled = 0;
+    for (int64_t oi = 0; oi < N; ++oi) {
+      const int32_t seed = order[oi];
+      if (seen[seed]) continue;
+      seen[seed] = 1;
+      int64_t head = filled;
+      node_perm[filled++] = seed;
+      while (head < filled) {
+        const int32_t u = node_perm[head++];
+        for (int32_t k = uptr[u]; k < uptr[u + 1]; ++k) {
+          const int32_t v = uadj[k];
+          if (!seen[v]) { seen[v] = 1; node_perm[filled++] = v; }
+        }
+      }
+    }
+  } else {
+    std::iota(node_perm.begin(), node_perm.end(), 0);
+  }
+  for (int64_t p = 0; p < N; ++p) node_inv[node_perm[p]] = (int32_t)p;
+  for (int64_t i = 0; i < E; ++i) { hs[i] = node_inv[hs[i]]; hd[i] = node_inv[hd[i]]; }
 
   // stable counting sort by dst -> internal order
   std::vector<int32_t> in_ptr((size_t)N + 1, 0), out_ptr((size_t)N + 1, 0);
@@ -184,6 +232,8 @@ int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
   if (e == cudaSuccess) e = up(&pl->out_dst, out_dst);
   if (e == cudaSuccess) e = up(&pl->perm, perm);
   if (e == cudaSuccess) e = up(&pl->inv_perm, inv);
+  if (e == cudaSuccess) e = up(&pl->node_perm, node_perm);
+  if (e == cudaSuccess) e = up(&pl->node_inv, node_inv);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // host staging vectors die at return
   if (e != cudaSuccess) {
     gg::free_plan(pl);
@@ -216,9 +266,10 @@ GG_PLAN_GET(gg_plan_out_eid, out_eid, const int32_t*, nullptr)
 int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream) {
   GG_REQUIRE(plan && out, "plan_copy_array: null pointer");
   const Plan* p = reinterpret_cast<const Plan*>(plan);
-  const int32_t* srcs[7] = {p->perm, p->inv_perm, p->src, p->dst, p->in_ptr, p->out_ptr, p->out_eid};
-  GG_REQUIRE(which >= 0 && which < 7, "plan_copy_array: bad selector");
-  const int64_t n = (which == 4 || which == 5) ? p->N + 1 : p->E;
+  const int32_t* srcs[9] = {p->perm, p->inv_perm, p->src, p->dst, p->in_ptr, p->out_ptr, p->out_eid,
+                            p->node_perm, p->node_inv};
+  GG_REQUIRE(which >= 0 && which < 9, "plan_copy_array: bad selector");
+  const int64_t n = (which == 4 || which == 5) ? p->N + 1 : (which >= 7 ? p->N : p->E);
   if (n > 0)
     GG_CUDA(cudaMemcpyAsync(out, srcs[which], n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return GG_OK;

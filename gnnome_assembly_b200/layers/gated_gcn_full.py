@@ -55,5 +55,6 @@ class GatedGCN_1d(nn.Module):
     def forward(self, g, h, e):
         plan = plan_for(g, h.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)
-        h, e_int = self.forward_internal(plan, h, e_int)
-        return h, GF.permute_rows(e_int, plan.inv_perm, plan.perm)
+        h, e_int = self.forward_internal(plan, GF.permute_rows(h, plan.node_perm, plan.node_inv), e_int)
+        return (GF.permute_rows(h, plan.node_inv, plan.node_perm),
+                GF.permute_rows(e_int, plan.inv_perm, plan.perm))

@@ -21,5 +21,6 @@ class GraphGatedGCN(nn.Module):
     def forward(self, graph, h, e):
         plan = plan_for(graph, h.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)      # once for the whole stack
-        h, e_int = self.forward_internal(plan, h, e_int)
-        return h, GF.permute_rows(e_int, plan.inv_perm, plan.perm)
+        h, e_int = self.forward_internal(plan, GF.permute_rows(h, plan.node_perm, plan.node_inv), e_int)
+        return (GF.permute_rows(h, plan.node_inv, plan.node_perm),
+                GF.permute_rows(e_int, plan.inv_perm, plan.perm))

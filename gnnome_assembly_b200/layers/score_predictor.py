@@ -24,5 +24,5 @@ class ScorePredictor(nn.Module):
     def forward(self, graph, x, e):
         plan = plan_for(graph, x.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)
-        s = self.forward_internal(plan, x, e_int)
+        s = self.forward_internal(plan, GF.permute_rows(x, plan.node_perm, plan.node_inv), e_int)
         return GF.permute_rows(s.unsqueeze(-1), plan.inv_perm, plan.perm)

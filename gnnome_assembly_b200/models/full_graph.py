@@ -25,6 +25,7 @@ class GraphGatedGCNModel(nn.Module):
     def forward(self, graph, x, e, pe):
         plan = plan_for(graph, pe.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)                       # E x 2, edge-id -> internal
+        pe = GF.permute_rows(pe, plan.node_perm, plan.node_inv)                    # N x 18, node id -> internal
         h = GF.linear(pe, self.linear_pe.weight, self.linear_pe.bias)              # full_graph.py:23 (x ignored)
         e_int = GF.edge_mlp(e_int, self.linear1_edge.weight, self.linear1_edge.bias,
                             self.linear2_edge.weight, self.linear2_edge.bias)      # :24-26

@@ -18,7 +18,7 @@ from . import _lib
 class GraphPlan:
     """Device-side CSR over in-edges (= internal edge order), CSR over out-edges, permutations."""
 
-    def __init__(self, src, dst, num_nodes, device=None):
+    def __init__(self, src, dst, num_nodes, device=None, relabel=True):
         src = torch.as_tensor(src)
         dst = torch.as_tensor(dst)
         if device is None:
@@ -36,9 +36,10 @@ class GraphPlan:
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.gg_plan_create(src32.data_ptr(), dst32.data_ptr(), self.num_nodes, self.num_edges, stream,
-                                    C.byref(handle))
-        _lib.check(rc, "gg_plan_create")
+            rc = lib.gg_plan_create_ex(src32.data_ptr(), dst32.data_ptr(), self.num_nodes, self.num_edges,
+                                       1 if relabel else 0, stream, C.byref(handle))
+        _lib.check(rc, "gg_plan_create_ex")
+        self.relabel = bool(relabel)
         self._handle = handle
         self._finalizer = weakref.finalize(self, lib.gg_plan_destroy, handle)
 
@@ -46,14 +47,16 @@ class GraphPlan:
     def handle(self):
         return self._handle
 
-    _WHICH = {"perm": 0, "inv_perm": 1, "src": 2, "dst": 3, "in_ptr": 4, "out_ptr": 5, "out_eid": 6}
+    _WHICH = {"perm": 0, "inv_perm": 1, "src": 2, "dst": 3, "in_ptr": 4, "out_ptr": 5, "out_eid": 6,
+              "node_perm": 7, "node_inv": 8}
 
     def array(self, name):
         """Copy of one of the plan's device index arrays as an int32 torch tensor (cached)."""
         cache = self.__dict__.setdefault("_arrays", {})
         if name not in cache:
             which = self._WHICH[name]
-            n = self.num_nodes + 1 if name in ("in_ptr", "out_ptr") else self.num_edges
+            n = (self.num_nodes + 1 if name in ("in_ptr", "out_ptr")
+                 else self.num_nodes if name in ("node_perm", "node_inv") else self.num_edges)
             out = torch.empty(n, dtype=torch.int32, device=self.device)
             if n > 0:
                 with torch.cuda.device(self.device):
@@ -71,6 +74,15 @@ class GraphPlan:
     @property
     def inv_perm(self):
         return self.array("inv_perm")
+
+    @property
+    def node_perm(self):
+        """int32[N]: internal node position -> caller node id (node features are permuted at the seam)."""
+        return self.array("node_perm")
+
+    @property
+    def node_inv(self):
+        return self.array("node_inv")
 
     @property
     def src(self):

@@ -56,6 +56,12 @@ int gg_profile_report(char* buf, size_t cap);
  * points into it.  Internal position p holds caller edge perm[p]. */
 int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
                    void* stream, gg_plan_t** out);
+/* flags: GG_PLAN_RELABEL (default of gg_plan_create) renumbers the nodes breadth-first so that the
+ * neighbours of a node are close in memory (assembly graphs are near-linear, read ids are arbitrary).
+ * Node features then live in INTERNAL node order: row p of h holds caller node node_perm[p]. */
+#define GG_PLAN_RELABEL 1
+int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges, int flags,
+                      void* stream, gg_plan_t** out);
 int gg_plan_destroy(gg_plan_t* plan);
 int64_t gg_plan_num_nodes(const gg_plan_t* plan);
 int64_t gg_plan_num_edges(const gg_plan_t* plan);
@@ -69,7 +75,8 @@ const int32_t* gg_plan_in_ptr(const gg_plan_t* plan);
 const int32_t* gg_plan_out_ptr(const gg_plan_t* plan);
 const int32_t* gg_plan_out_eid(const gg_plan_t* plan);
 /* copy one of those arrays into a caller-owned device buffer (async on `stream`);
- * which: 0 perm, 1 inv_perm, 2 src, 3 dst, 4 in_ptr, 5 out_ptr, 6 out_eid */
+ * which: 0 perm, 1 inv_perm, 2 src, 3 dst, 4 in_ptr, 5 out_ptr, 6 out_eid, 7 node_perm[N] (internal ->
+ * caller node id), 8 node_inv[N] */
 int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream);
 
 /* ---- dense linear ( nn.Linear ) -----------------------------------------------------------

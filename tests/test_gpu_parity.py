@@ -34,7 +34,8 @@ def test_plan_arrays(n, m):
     rng = np.random.default_rng(n + m)
     src = rng.integers(0, n, m).astype(np.int32)
     dst = rng.integers(0, n, m).astype(np.int32)
-    plan = GraphPlan(torch.from_numpy(src), torch.from_numpy(dst), n, dev)
+    plan = GraphPlan(torch.from_numpy(src), torch.from_numpy(dst), n, dev, relabel=False)
+    assert np.array_equal(plan.node_perm.cpu().numpy(), np.arange(n))
     perm = plan.perm.cpu().numpy()
     assert np.array_equal(perm, np.argsort(dst, kind="stable"))
     assert np.array_equal(plan.inv_perm.cpu().numpy()[perm], np.arange(m))
@@ -50,6 +51,45 @@ def test_plan_arrays(n, m):
     for u in range(min(n, 50)):
         seg = out_eid[out_ptr[u]:out_ptr[u + 1]]
         assert np.all(isrc[seg] == u) and np.all(np.diff(seg) > 0)
+
+
+@pytest.mark.parametrize("n,m", [(7, 0), (96, 700), (5000, 40000)])
+def test_plan_relabelled(n, m):
+    """Breadth-first node relabelling: a permutation of the nodes; every array is consistent with it."""
+    dev = _dev()
+    from gnnome_assembly_b200 import GraphPlan
+    rng = np.random.default_rng(n * 7 + m)
+    src = rng.integers(0, n, m).astype(np.int32)
+    dst = rng.integers(0, n, m).astype(np.int32)
+    plan = GraphPlan(torch.from_numpy(src), torch.from_numpy(dst), n, dev)
+    node_perm = plan.node_perm.cpu().numpy()
+    node_inv = plan.node_inv.cpu().numpy()
+    assert np.array_equal(np.sort(node_perm), np.arange(n))
+    assert np.array_equal(node_inv[node_perm], np.arange(n))
+    perm = plan.perm.cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(m))
+    isrc, idst = plan.src.cpu().numpy(), plan.dst.cpu().numpy()
+    assert np.array_equal(isrc, node_inv[src[perm]]) and np.array_equal(idst, node_inv[dst[perm]])
+    assert np.all(np.diff(idst) >= 0)
+    in_ptr = plan.array("in_ptr").cpu().numpy()
+    assert np.array_equal(np.diff(in_ptr), np.bincount(idst, minlength=n))
+    out_ptr, out_eid = plan.array("out_ptr").cpu().numpy(), plan.array("out_eid").cpu().numpy()
+    assert np.array_equal(np.diff(out_ptr), np.bincount(isrc, minlength=n))
+    assert np.array_equal(np.sort(out_eid), np.arange(m))
+    assert np.array_equal(isrc[out_eid], np.repeat(np.arange(n), np.diff(out_ptr)))
+
+
+def test_plan_relabel_gives_locality():
+    """On an assembly graph (random read ids) the relabelled order puts neighbours close together."""
+    dev = _dev()
+    from gnnome_assembly_b200 import GraphPlan
+    from gnnome_assembly_b200.synth import make_assembly_graph
+    g = make_assembly_graph("chr19", seed=2, genome_len=3_000_000)
+    plan = GraphPlan(torch.from_numpy(g.src), torch.from_numpy(g.dst), g.num_nodes, dev)
+    isrc, idst = plan.src.cpu().numpy().astype(np.int64), plan.dst.cpu().numpy().astype(np.int64)
+    y = g.y[plan.perm.cpu().numpy()] > 0                                  # true overlaps only (no random repeats)
+    assert np.median(np.abs(isrc - idst)[y]) < 64
+    assert np.median(np.abs(g.src.astype(np.int64) - g.dst)[g.y > 0]) > 500
 
 
 def test_plan_rejects_bad_index():
