@@ -100,52 +100,6 @@ __device__ __forceinline__ void block_flush_stats(const double (&s1)[D / 32], co
   }
 }
 
-
-// Grid-stride walk over the nodes of one warp with the index chain taken off the critical path: the CSR
-// pointers of node k+2 and the first 32 edge indices of node k+1 are loaded while node k is processed, so a
-// node costs one row-gather latency instead of pointer -> index -> row.
-template <int NIDX>      // number of per-edge index arrays to pre-load (0, 1 or 2)
-struct NodeWalker {
-  const int32_t* ptr; const int32_t* idx_a; const int32_t* idx_b;
-  int64_t N, nw, u, u1, u2;
-  int beg, end, beg1, end1, beg2, end2;
-  int ia, ib, ia1, ib1;            // this lane's index of edge (beg + lane) for the current / next node
-  int lane;
-
-  __device__ __forceinline__ void load_ptr(int64_t node, int& b, int& e) const {
-    if (node < N) { b = __ldg(ptr + node); e = __ldg(ptr + node + 1); } else { b = 0; e = 0; }
-  }
-  __device__ __forceinline__ void load_idx(int b, int e, int& a, int& c) const {
-    a = 0; c = 0;
-    if constexpr (NIDX > 0) {
-      if (lane < e - b) { a = __ldg(idx_a + b + lane); if constexpr (NIDX > 1) c = __ldg(idx_b + b + lane); }
-    }
-  }
-  __device__ __forceinline__ void init(const int32_t* p, const int32_t* a, const int32_t* b, int64_t n, int64_t gw,
-                                       int64_t nwarps, int ln) {
-    ptr = p; idx_a = a; idx_b = b; N = n; nw = nwarps; lane = ln;
-    u = gw; u1 = gw + nw; u2 = gw + 2 * nw;
-    load_ptr(u, beg, end);
-    load_ptr(u1, beg1, end1);
-    load_idx(beg, end, ia, ib);
-  }
-  __device__ __forceinline__ bool valid() const { return u < N; }
-  // call at the top of the loop body: issues the prefetches for the following nodes
-  __device__ __forceinline__ void prefetch() {
-    load_ptr(u2, beg2, end2);
-    load_idx(beg1, end1, ia1, ib1);
-  }
-  // indices of edges [base, base+32) of the current node (base == beg comes from the prefetched registers)
-  __device__ __forceinline__ void chunk(int base, int& a, int& b) const {
-    if (base == beg) { a = ia; b = ib; } else { load_idx(base, end, a, b); }
-  }
-  __device__ __forceinline__ void advance() {
-    u = u1; u1 = u2; u2 += nw;
-    beg = beg1; end = end1; beg1 = beg2; end1 = end2;
-    ia = ia1; ib = ib1;
-  }
-};
-
 // =====================================================================================  FORWARD
 // F3: per dst node v, over its in-edges i (s_i -> v):
 //   n = norm_e(t_i); e_out_i = relu(n) + e_in_i; sigma = sigmoid(e_out_i)           (:122-127)
@@ -165,18 +119,13 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
   nrm.init(stats, E > 0 ? 1.0 / (double)E : 0.0, gamma, beta, lane);
   float* hf = agg;
   float* invden_f = agg + 2 * N * D;
-  NodeWalker<1> wk;
-  wk.init(in_ptr, src, nullptr, N, gw, nw, lane);
-  for (; wk.valid(); wk.advance()) {
-    wk.prefetch();
-    const int64_t v = wk.u;
-    const int beg = wk.beg, end = wk.end;
+  for (int64_t v = gw; v < N; v += nw) {
+    const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> num, den;
     num.fill(0.f); den.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_s, unused_;
-      wk.chunk(base, my_s, unused_);
+      const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
       for (int j = 0; j < cnt; j += 2) {
         const bool two = (j + 1) < cnt;
         const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
@@ -244,18 +193,14 @@ node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
   double s1[VPL], s2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
-  NodeWalker<2> wk;
-  wk.init(out_ptr, out_eid, out_dst, N, gw, nw, lane);
-  for (; wk.valid(); wk.advance()) {
-    wk.prefetch();
-    const int64_t u = wk.u;
-    const int beg = wk.beg, end = wk.end;
+  for (int64_t u = gw; u < N; u += nw) {
+    const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> num, den;
     num.fill(0.f); den.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_i, my_v;
-      wk.chunk(base, my_i, my_v);
+      const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
+      const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
       for (int j = 0; j < cnt; j += 4) {
         // four out-edges in flight: all row gathers are issued before any math
         Row<D> eo[4], a3[4];
@@ -436,12 +381,8 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
   float f1[VPL], f2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
-  NodeWalker<1> wk;
-  wk.init(in_ptr, src, nullptr, N, gw, nw, lane);
-  for (; wk.valid(); wk.advance()) {
-    wk.prefetch();
-    const int64_t v = wk.u;
-    const int beg = wk.beg, end = wk.end;
+  for (int64_t v = gw; v < N; v += nw) {
+    const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> gnf, gdf, a3, acc;
     acc.fill(0.f);
     if (beg < end) {
@@ -468,8 +409,7 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
     };
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_s, unused_;
-      wk.chunk(base, my_s, unused_);
+      const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
       for (int j = 0; j < cnt; j += 2) {
         const bool two = (j + 1) < cnt;
         const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
@@ -526,12 +466,8 @@ edge_bwd_b_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
     m1[k] = (float)(bstats_e[c] * inv_e);
     m2[k] = (float)(bstats_e[D + c] * inv_e);
   }
-  NodeWalker<0> wk;
-  wk.init(in_ptr, nullptr, nullptr, N, gw, nw, lane);
-  for (; wk.valid(); wk.advance()) {
-    wk.prefetch();
-    const int64_t v = wk.u;
-    const int beg = wk.beg, end = wk.end;
+  for (int64_t v = gw; v < N; v += nw) {
+    const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> acc;
     acc.fill(0.f);
     for (int64_t i = beg; i < end; i += 2) {
@@ -576,18 +512,14 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * kNodeThreads) >> 5;
   const float* Gf = G;
-  NodeWalker<2> wk;
-  wk.init(out_ptr, out_eid, out_dst, N, gw, nw, lane);
-  for (; wk.valid(); wk.advance()) {
-    wk.prefetch();
-    const int64_t u = wk.u;
-    const int beg = wk.beg, end = wk.end;
+  for (int64_t u = gw; u < N; u += nw) {
+    const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> acc1, acc2;
     acc1.fill(0.f); acc2.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      int my_i, my_v;
-      wk.chunk(base, my_i, my_v);
+      const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
+      const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
       for (int j = 0; j < cnt; j += 4) {
         Row<D> gt[4], eo[4], gnf[4];
 #pragma unroll
