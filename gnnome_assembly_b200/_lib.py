@@ -44,6 +44,10 @@ SIGNATURES = {
     "gg_layer_bwd": (_i, [_p, _i, _i, _i] + [_p] * 32),
     "gg_score_fwd": (_i, [_p, _i, _i] + [_p] * 11),
     "gg_score_bwd": (_i, [_p, _i, _i] + [_p] * 18),
+    "gg_prep_edge_features": (_i, [_i64, _p, _p, _p, _p, _p]),
+    "gg_prep_pe": (_i, [_p, _i, C.c_double, _p, _p, _p]),
+    "gg_bce_metrics_fwd": (_i, [_i64, _p, _p, C.c_float, _p, _p]),
+    "gg_bce_bwd": (_i, [_i64, _p, _p, C.c_float, _p, _p, _p]),
     "gg_gather_rows": (_i, [_i64, _i, _p, _p, _p, _p]),
 }
 

@@ -135,6 +135,24 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
                  float* g_e, float* dWq, float* dbq, float* dW1e, float* dw2, float* db2, float* g_pre,
                  float* gQ, double* red, void* stream);
 
+/* ---- input preparation ("next" row 1 of SURVEY.md 8f) ----------------------------------------------
+ * gg_prep_edge_features replaces utils.preprocess_graph, utils.py:70-74: e[E,2] = z-scored overlap_length,
+ * overlap_similarity (mean / unbiased std per graph), caller edge order in and out.  ws: 4 doubles.
+ * gg_prep_pe replaces utils.add_positional_encoding, utils.py:102-138 (type_pe == 'PR') and the concat of
+ * train.py:249-251: pe[N, 2 + pe_dim] = in_degree | out_degree | pe_dim PageRank iterates (alpha = 0.95 in the
+ * reference), fp64 internally like scipy, rows in CALLER node order.  ws: 3N doubles. */
+int gg_prep_edge_features(int64_t E, const float* overlap_length, const float* overlap_similarity, float* e_out,
+                          double* ws, void* stream);
+int gg_prep_pe(const gg_plan_t* plan, int pe_dim, double alpha, float* pe_out, double* ws, void* stream);
+
+/* ---- fused loss + metrics ("next" row 2 of SURVEY.md 8f) -----------------------------------------------
+ * Replaces BCEWithLogitsLoss(pos_weight) (train.py:211,255) and utils.calculate_tfpn (utils.py:217-223),
+ * four .item() syncs per step in the reference.  out5 (doubles): sum of per-edge losses | TP | TN | FP | FN.
+ * gg_bce_bwd: g_scores[i] = g_loss[0] / E * d(loss_i)/d(score_i)  (mean reduction). */
+int gg_bce_metrics_fwd(int64_t E, const float* scores, const float* y, float pos_weight, double* out5, void* stream);
+int gg_bce_bwd(int64_t E, const float* scores, const float* y, float pos_weight, const float* g_loss,
+               float* g_scores, void* stream);
+
 /* ---- edge-order helpers ------------------------------------------------------------------------
  * out[p, :] = in[idx[p], :]  (rows of `width` floats).  Used to move e[E,2] / scores[E] between the
  * caller's edge-id order (the contract at the model boundary) and the internal order. */

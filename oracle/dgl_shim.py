@@ -73,6 +73,21 @@ class DGLGraph:
     def device(self):
         return self._src.device
 
+    def int(self):                                       # utils.py:68
+        return self
+
+    def in_degrees(self):                                # utils.py:102
+        return torch.bincount(self._dst, minlength=self._n)
+
+    def out_degrees(self):                               # utils.py:103
+        return torch.bincount(self._src, minlength=self._n)
+
+    def adjacency_matrix(self, scipy_fmt="csr"):         # utils.py:124 (DGL < 1.0): A[u, v] = #edges u -> v
+        import numpy as np
+        import scipy.sparse as sp
+        A = sp.coo_matrix((np.ones(self.num_edges()), (self._src.numpy(), self._dst.numpy())), shape=(self._n, self._n))
+        return A.asformat(scipy_fmt)
+
     @contextlib.contextmanager
     def local_scope(self):
         nd, ed = dict(self.ndata), dict(self.edata)

@@ -68,7 +68,34 @@ def run_case(name, graph, d, L, batch_norm, seed, state_dict=None, with_grads=Tr
     print(f"{name}: N={graph.num_nodes} E={graph.num_edges} |scores|max={scores.abs().max():.4f}")
 
 
+def run_prep_case():
+    """The reference's own utils.preprocess_graph / add_positional_encoding / calculate_tfpn (utils.py)."""
+    import utils  # noqa: E402  (the reference's module)
+    gsyn = make_assembly_graph("chr19", seed=11, genome_len=500_000)
+    src = torch.from_numpy(gsyn.src.astype(np.int64))
+    dst = torch.from_numpy(gsyn.dst.astype(np.int64))
+    g = dgl.graph((src, dst), num_nodes=gsyn.num_nodes)
+    g.edata["overlap_length"] = torch.from_numpy(gsyn.overlap_length.astype(np.int64))
+    g.edata["overlap_similarity"] = torch.from_numpy(gsyn.overlap_similarity)
+    g.edata["y"] = torch.from_numpy(gsyn.y)
+    g = utils.preprocess_graph(g, "", 0)
+    g = utils.add_positional_encoding(g, 16)
+    pe = torch.cat((g.ndata["in_deg"].unsqueeze(1), g.ndata["out_deg"].unsqueeze(1), g.ndata["pe"]), dim=1)  # train.py:249-251
+    torch.manual_seed(4)
+    scores = torch.randn(gsyn.num_edges) * 2
+    scores[:5] = 0.0                                      # sigmoid == 0.5 exactly -> rounds to 0
+    tfpn = utils.calculate_tfpn(scores, g.edata["y"])
+    pw = 1.0 / 16.5
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw]))(scores, g.edata["y"])
+    torch.save({"src": gsyn.src.copy(), "dst": gsyn.dst.copy(), "num_nodes": gsyn.num_nodes,
+                "overlap_length": gsyn.overlap_length.copy(), "overlap_similarity": gsyn.overlap_similarity.copy(),
+                "y": gsyn.y.copy(), "e": g.edata["e"].clone(), "pe": pe.clone(), "scores": scores, "tfpn": tfpn,
+                "pos_weight": pw, "loss": float(loss)}, os.path.join(HERE, "ref_prep_small.pt"))
+    print(f"ref_prep_small: N={gsyn.num_nodes} E={gsyn.num_edges} tfpn={tfpn} loss={float(loss):.6f}")
+
+
 if __name__ == "__main__":
+    run_prep_case()
     small = make_random_graph(96, 700, seed=3, isolated_frac=0.15)
     run_case("ref_rand_d64_L2_bn", small, 64, 2, True, seed=0)
     run_case("ref_rand_d64_L2_ln", small, 64, 2, False, seed=1)
