@@ -56,12 +56,14 @@ __global__ void zscore_sq_kernel(int64_t E, const float* __restrict__ a, const f
 }
 __global__ void zscore_apply_kernel(int64_t E, const float* __restrict__ a, const float* __restrict__ b,
                                     const double* __restrict__ ws, float* __restrict__ out) {
-  // torch: (x - x.mean()) / x.std()  in fp32, std unbiased (utils.py:72-73)
-  const float ma = (float)(ws[0] / (double)E), mb = (float)(ws[1] / (double)E);
-  const float sa = (float)sqrt(ws[2] / (double)(E - 1)), sb = (float)sqrt(ws[3] / (double)(E - 1));
+  // torch: (x - x.mean()) / x.std(), std unbiased (utils.py:72-73).  The reference does this in fp32, where
+  // x - mean cancels badly for overlap_similarity (values in [0.99, 1]); here the subtraction and division
+  // are done in fp64 and rounded once, so the result is the correctly rounded z-score.
+  const double ma = ws[0] / (double)E, mb = ws[1] / (double)E;
+  const double ia = 1.0 / sqrt(ws[2] / (double)(E - 1)), ib = 1.0 / sqrt(ws[3] / (double)(E - 1));
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
-    out[2 * i + 0] = (a[i] - ma) / sa;
-    out[2 * i + 1] = (b[i] - mb) / sb;
+    out[2 * i + 0] = (float)(((double)a[i] - ma) * ia);
+    out[2 * i + 1] = (float)(((double)b[i] - mb) * ib);
   }
 }
 
