@@ -115,7 +115,8 @@ def make_assembly_graph(chrom="chr19", seed=0, genome_len=None, target_edges=Non
     e = np.stack([ol_z, sim_z], axis=1).astype(np.float32)
     in_deg = np.bincount(dst, minlength=N).astype(np.float32)
     out_deg = np.bincount(src, minlength=N).astype(np.float32)
-    pe = np.concatenate([in_deg[:, None], out_deg[:, None], pagerank_pe(src, dst, N, pe_dim)], axis=1)
+    pr = pagerank_pe(src, dst, N, pe_dim) if pe_dim > 0 else np.zeros((N, 0), np.float32)   # pe_dim=0: structure only
+    pe = np.concatenate([in_deg[:, None], out_deg[:, None], pr], axis=1)
     return SynthGraph(src.astype(np.int32), dst.astype(np.int32), N, e, pe.astype(np.float32), y,
                       ol.astype(np.float32), sim.astype(np.float32))
 
