@@ -45,14 +45,16 @@ def test_gpu_zscore_matches_reference(gold):
     dev = _dev()
     from gnnome_assembly_b200 import prep
     e = prep.preprocess_features(torch.from_numpy(gold["overlap_length"]).to(dev), torch.from_numpy(gold["overlap_similarity"]).to(dev))
-    # bar: the reference subtracts an fp32 mean; for overlap_similarity (values in [0.99, 1], std 0.003) a
-    # 1-ulp difference of that mean (6e-8) is amplified by 1/std to ~2e-5 in the z-score.  Our mean is the
-    # correctly rounded fp64 one, so we hold column 0 to 2e-6 and column 1 to 5e-5 (absolute, |z| ~ 1).
-    assert torch.allclose(e.cpu()[:, 0], gold["e"][:, 0], rtol=2e-6, atol=2e-6)
-    assert torch.allclose(e.cpu()[:, 1], gold["e"][:, 1], rtol=0, atol=5e-5)
+    # bar: the reference computes (x - mean) / std in fp32.  For overlap_similarity (values in [0.99, 1], std
+    # 0.003) the fp32 mean carries a few ulps (~3e-7) of summation error which x - mean amplifies by 1/std to
+    # ~1e-4 in the z-score: that is noise of the reference, not signal.  The kernel does the subtraction and
+    # division in fp64 and rounds once, so it is held (a) to the exact fp64 value within fp32 rounding and
+    # (b) to the reference's values within that noise (column 0: 2e-6, column 1: 3e-4, absolute, |z| ~ 1).
     ref64 = np.stack([(a - a.mean()) / a.std(ddof=1) for a in
                       (gold["overlap_length"].astype(np.float64), gold["overlap_similarity"].astype(np.float64))], 1)
-    assert np.abs(e.cpu().numpy() - ref64).max() < 5e-6                  # and within fp32 rounding of the exact value
+    assert np.abs(e.cpu().numpy() - ref64).max() < 5e-7
+    assert torch.allclose(e.cpu()[:, 0], gold["e"][:, 0], rtol=2e-6, atol=2e-6)
+    assert torch.allclose(e.cpu()[:, 1], gold["e"][:, 1], rtol=0, atol=3e-4)
 
 
 @pytest.mark.gpu
