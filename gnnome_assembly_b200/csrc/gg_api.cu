@@ -161,16 +161,34 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   edge_bwd_a_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
                                                            gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D);
   GG_KERNEL_END("edge_bwd_a_kernel", st);
-  GG_KERNEL_BEGIN("edge_bwd_b_kernel", st);
-  edge_bwd_b_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
-                                                           gamma_e, beta_e, g_t, gP);
-  GG_KERNEL_END("edge_bwd_b_kernel", st);
+  int rc;
+  // Batch norm + tensor-core path: g_t is produced inside the bwd-data GEMM (A-operand transform), so the
+  // edge_bwd_b pass (read t, g_eo; write g_t) does not exist; gB2h is finished per node in edge_bwd_src.
+  const bool fused_gt = (NORM == GG_NORM_BATCH) && g_tc_mode && E > 0 && D <= 256 && residual &&
+                        g_e_in != g_eo &&      // the GEMM re-reads g_eo rows as its A operand: no in-place output
+                        tc::eligible(false, true, E, D, D, D, D, g_eo, B3);
+  if (fused_gt) {
+    EpiAddMaskT<true, false> epi{g_e_in, (int64_t)D, g_eo, nullptr};
+    tc::BnBwdATx atx{stats, bstats + 2 * D, gamma_e, beta_e, 1.0 / (double)E, g_t, (int64_t)D};
+    rc = tc::launch<false, true, false, false>("gemm_bwd_e_in", g_eo, D, B3, D, E, D, D, 1, nullptr, nullptr, epi,
+                                               sm_count(), st, atx, t);
+    if (rc) return rc;
+  } else {
+    GG_KERNEL_BEGIN("edge_bwd_b_kernel", st);
+    edge_bwd_b_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
+                                                             gamma_e, beta_e, g_t, gP);
+    GG_KERNEL_END("edge_bwd_b_kernel", st);
+  }
   GG_KERNEL_BEGIN("edge_bwd_src_kernel", st);
-  edge_bwd_src_kernel<D><<<grid, kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP);
+  edge_bwd_src_kernel<D><<<grid, kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP,
+                                                       fused_gt ? 1 : 0, E, pl->in_ptr, agg + 4 * N * D, stats,
+                                                       bstats + 2 * D, gamma_e);
   GG_KERNEL_END("edge_bwd_src_kernel", st);
   // g_e_in = g_eo (residual) + g_t B3 ; dB3 = g_t^T e_in ; db3 = colsum g_t
-  int rc = linear_bwd_data("gemm_bwd_e_in", E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
-  if (rc) return rc;
+  if (!fused_gt) {
+    rc = linear_bwd_data("gemm_bwd_e_in", E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
+    if (rc) return rc;
+  }
   rc = linear_bwd_weight("gemm_dB3", E, D, D, g_t, D, e_in, D, dB3, db3, st);
   if (rc) return rc;
   // g_h_in = g_h (residual) + gP Wn ; dWn = gP^T h_in ; dbn = colsum gP

@@ -34,15 +34,21 @@ namespace gg {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                         // (3 when the A operand is built from two streamed tiles)
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo   (+ a second A tile with an A transform)
+constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;  // 192 KB either way (4 x 48 KB or 3 x 64 KB)
+constexpr int COEF_BYTES = 6 * 256 * 4;           // A-transform coefficient vectors (6 x K floats, K <= 256)
 constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
 constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
 constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
 constexpr int IDX_BYTES = 2 * 2 * 2 * BM * 4;     // per epilogue group, double buffered: src / dst node ids of 128 rows
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + STATS_BYTES + IDX_BYTES + BAR_BYTES;
+template <bool kStats, class Epi, class ATx>
+constexpr int smem_bytes() {
+  return 1024 /*align slack*/ + PIPE_BYTES + STAGING_BYTES + (kStats ? STATS_BYTES : 0) + (Epi::kIdx ? IDX_BYTES : 0) +
+         BAR_BYTES + (ATx::kActive ? COEF_BYTES : 0);
+}
 constexpr int THREADS = 512;
 constexpr int TMEM_COLS = 512;                    // 2 x 128 accumulator columns + 4 stages x (32 hi + 32 lo) A columns
 constexpr int TMEM_A0 = 256;
@@ -179,16 +185,40 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// ---------------------------------------------------------------------------------- A-operand transforms
+// The converter owns whole A rows in registers on their way to TMEM, so an element-wise producer of the A
+// operand can be fused there instead of materialising A in HBM first.
+struct NoATx { static constexpr bool kActive = false; };
+
+// Batch-norm backward of the edge gate (layers/gated_gcn_full.py:122-123 differentiated): the A operand of
+// g_e_in = g_eo + g_t B3 is  g_t = gamma rstd (g_n - m1 - xhat m2),  g_n = g_eo [n > 0],  xhat = (t - mean) rstd,
+// n = gamma xhat + beta, built from the streamed tiles of g_eo (TMA map A) and t (TMA map A2).  The converter
+// also stores g_t (the weight-gradient GEMM and the out-edge pass read it), so the separate edge_bwd_b pass
+// (read t, g_eo; write g_t) disappears.
+struct BnBwdATx {
+  static constexpr bool kActive = true;
+  const double* stats;      // [2K] sum t, sum t^2
+  const double* bstats;     // [2K] sum g_n, sum g_n xhat
+  const float* gamma; const float* beta;
+  double inv_count;         // 1 / E
+  float* g_t; int64_t ld;
+};
+
 // ---------------------------------------------------------------------------------- the kernel
-template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi>
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Args g, Epi epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, Args g, Epi epi, ATx atx) {
+  static_assert(!ATx::kActive || !A_MN, "A transforms are written for K-major A");
+  constexpr int kStages = ATx::kActive ? 3 : 4;
+  constexpr int kStageBytes = (ATx::kActive ? 4 : 3) * TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
-  constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + STATS_BYTES,
-                OFF_BAR = OFF_IDX + IDX_BYTES;
+  constexpr int OFF_STG = PIPE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
+                OFF_BAR = OFF_IDX + (Epi::kIdx ? IDX_BYTES : 0), OFF_COEF = OFF_BAR + BAR_BYTES;
+  float* coef = reinterpret_cast<float*>(gen + OFF_COEF);     // [6][K]: mean, rstd, gamma, beta, m1, m2 (ATx only)
   float* staging = reinterpret_cast<float*>(gen + OFF_STG);
   double* sstat = reinterpret_cast<double*>(gen + OFF_STAT);
   int* sidx = reinterpret_cast<int*>(gen + OFF_IDX);
@@ -207,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int64_t total_work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), 128); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), 128); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,8 +245,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 8) {
-    for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 256) sstat[i] = 0.0;
+  if constexpr (kStats) {
+    if (warp >= 8) {
+      for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 256) sstat[i] = 0.0;
+    }
+  }
+  if constexpr (ATx::kActive) {
+    const int K = (int)g.K;
+    for (int c = threadIdx.x; c < K; c += THREADS) {
+      const double m = atx.stats[c] * atx.inv_count;
+      double var = atx.stats[K + c] * atx.inv_count - m * m;
+      var = var > 0.0 ? var : 0.0;
+      coef[0 * K + c] = (float)m;
+      coef[1 * K + c] = (float)(1.0 / sqrt(var + (double)kNormEps));
+      coef[2 * K + c] = __ldg(atx.gamma + c);
+      coef[3 * K + c] = __ldg(atx.beta + c);
+      coef[4 * K + c] = (float)(atx.bstats[c] * atx.inv_count);
+      coef[5 * K + c] = (float)(atx.bstats[K + c] * atx.inv_count);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -247,8 +293,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty(s), ph ^ 1u);
-          const uint32_t st = stage0 + s * STAGE_BYTES;
-          mbar_expect_tx(full_raw(s), 2 * TILE_BYTES);
+          const uint32_t st = stage0 + s * kStageBytes;
+          mbar_expect_tx(full_raw(s), (ATx::kActive ? 3 : 2) * TILE_BYTES);
+          if constexpr (ATx::kActive) tma_load_2d(st + 3 * TILE_BYTES, &tmA2, full_raw(s), (int)(kbeg + (int64_t)kb * BK), mt * BM);
           const int k0 = (int)(kbeg + (int64_t)kb * BK);
           if constexpr (!A_MN) {
             tma_load_2d(st, &tmA, full_raw(s), k0, mt * BM);
@@ -262,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
           }
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -278,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_ab(s), ph);
           tc_fence_after();
-          const uint32_t st = stage0 + s * STAGE_BYTES;
+          const uint32_t st = stage0 + s * kStageBytes;
           const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A0 + 64 * s), a_lo = a_hi + 32;
           const uint64_t b_hi = make_desc<B_MN>(st + TILE_BYTES);
           const uint64_t b_lo = make_desc<B_MN>(st + 2 * TILE_BYTES);
@@ -291,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_tf32_ts(d_tmem, a_hi + 8 * ks, b_hi + ks * b_step, idesc, 1u);
           }
           umma_commit(empty(s));                       // frees the stage (smem B, TMEM A) when these MMAs are done
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
         umma_commit(tmem_full(acc));                   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
@@ -309,7 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float bsum = 0.f;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_raw(s), ph);
-        const uint8_t* st = gen + s * STAGE_BYTES;
+        const uint8_t* st = gen + s * kStageBytes;
         // ---- A row t of this K-block -> registers (k order), hi = raw bits, lo = x - trunc(x)
         uint32_t hi[32], lo[32];
         if constexpr (!A_MN) {
@@ -320,6 +367,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 x = row[c ^ (t & 7)];
             hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
             hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+          }
+          if constexpr (ATx::kActive) {
+            // hi[] holds g_eo[row, c0 .. c0+31]; the second tile holds t: build g_t in place and store it
+            const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
+            const int K = (int)g.K;
+            const int c0 = (int)(kbeg + (int64_t)kb * BK);
+            const int64_t m = (int64_t)mt * BM + t;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 tv = row2[c ^ (t & 7)];
+              const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+              float gt[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ch = c0 + 4 * c + j;
+                const float rs = coef[1 * K + ch], gm = coef[2 * K + ch];
+                const float xh = (tt[j] - coef[0 * K + ch]) * rs;
+                const float nv = xh * gm + coef[3 * K + ch];
+                const float gn = nv > 0.f ? __uint_as_float(hi[4 * c + j]) : 0.f;
+                gt[j] = gm * rs * (gn - coef[4 * K + ch] - xh * coef[5 * K + ch]);
+                hi[4 * c + j] = __float_as_uint(gt[j]);
+              }
+              if (nt == 0 && m < g.M)
+                *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + c0 + 4 * c) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+            }
           }
         } else {
           // MN-major 128B_ATOM_32B tile: box t/32 (4 KB), k-row k at k*128 B, m' = t%32 lives in 32-byte chunk
@@ -359,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         proxy_fence_async();                           // generic-proxy smem writes -> visible to the tensor core
         mbar_arrive(full_ab(s));
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       if constexpr (kBiasGrad) {
         const int64_t m = (int64_t)mt * BM + t;
@@ -582,15 +654,24 @@ inline bool eligible(bool a_mn, bool b_mn, int64_t M, int N, int64_t K, int64_t 
 }
 
 // C[M,N] = sum_k A(m,k) B(k,n).  A_MN: A stored [K, M] (lda) else [M, K];  B_MN: B stored [K, N] (ldb) else [N, K].
-template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi>
+// With an A transform, A2 is a second [M, K] operand streamed next to A (same lda).
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx = NoATx>
 int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
-           int splits, double* col_stats, float* bias_grad, const Epi& epi, int num_sms, cudaStream_t st) {
-  CUtensorMap tmA, tmB;
+           int splits, double* col_stats, float* bias_grad, const Epi& epi, int num_sms, cudaStream_t st,
+           const ATx& atx = ATx{}, const float* A2 = nullptr) {
+  CUtensorMap tmA, tmB, tmA2;
   int rc;
   if (A_MN) rc = make_map(&tmA, A, M, K, lda, 32, true); else rc = make_map(&tmA, A, K, M, lda, BM, false);
   if (rc) return rc;
   if (B_MN) rc = make_map(&tmB, B, N, K, ldb, 32, true); else rc = make_map(&tmB, B, K, N, ldb, BN, false);
   if (rc) return rc;
+  if (ATx::kActive) {
+    if (K > 256) { set_error("gnnome_b200: A transform supports K <= 256"); return GG_ERR_UNSUPPORTED; }
+    rc = make_map(&tmA2, A2, K, M, lda, BM, false);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+  }
   Args g{};
   g.M = M; g.N = N; g.K = K;
   g.m_tiles = (int)((M + BM - 1) / BM);
@@ -605,14 +686,15 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   g.dbg = tc_dbg_ref();
   const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
   const int grid = (int)(work < num_sms ? work : num_sms);
-  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx>;
+  constexpr int kSmem = smem_bytes<kStats, Epi, ATx>();
   static bool attr_set = false;      // one static per template instantiation
   if (!attr_set) {
-    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   GG_KERNEL_BEGIN(tag, st);
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, g, epi);
+  kern<<<grid, THREADS, kSmem, st>>>(tmA, tmB, tmA2, g, epi, atx);
   GG_KERNEL_END(tag, st);
   return GG_OK;
 }

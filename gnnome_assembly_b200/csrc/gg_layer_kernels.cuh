@@ -119,10 +119,11 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
   nrm.init(stats, E > 0 ? 1.0 / (double)E : 0.0, gamma, beta, lane);
   float* hf = agg;
   float* invden_f = agg + 2 * N * D;
+  float* sum_xhat = agg + 4 * N * D;      // sum over in-edges of xhat_e: lets the backward rebuild gB2h per node
   for (int64_t v = gw; v < N; v += nw) {
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
-    Row<D> num, den;
-    num.fill(0.f); den.fill(0.f);
+    Row<D> num, den, sx;
+    num.fill(0.f); den.fill(0.f); sx.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
       const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
@@ -140,6 +141,10 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
         a21.load(P + sb * (5 * D) + D, lane);
         nrm.normalize(x0);
         nrm.normalize(x1);
+        if constexpr (NORM == GG_NORM_BATCH) {
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) sx.v[k] += x0.v[k] + (two ? x1.v[k] : 0.f);
+        }
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
           const float nv = x0.v[k] * nrm.gamma[k] + nrm.beta[k];
@@ -171,6 +176,7 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
     }
     num.store(hf + v * D, lane);
     den.store(invden_f + v * D, lane);
+    if constexpr (NORM == GG_NORM_BATCH) sx.store(sum_xhat + v * D, lane);
   }
 }
 
@@ -363,7 +369,7 @@ node_bwd_apply_kernel(int64_t N, const float* __restrict__ z, const float* __res
 //   g_n  = g_eo*[n>0];  bstats_e += [g_n | g_n*xhat_e]
 //   gA3h[v] = sum_i sigma_i * gnb[s_i]              -> gP[v, 2d:3d]
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads)
+__global__ void __launch_bounds__(kNodeThreads, D <= 128 ? 2 : 1)
 edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ src,
                   const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ g_e,
                   const float* __restrict__ P, const float* __restrict__ G, const double* __restrict__ stats_e,
@@ -383,8 +389,8 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
   for (int k = 0; k < VPL; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
   for (int64_t v = gw; v < N; v += nw) {
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
-    Row<D> gnf, gdf, a3, acc;
-    acc.fill(0.f);
+    Row<D> gnf, gdf, a3, acc, sgn;
+    acc.fill(0.f); sgn.fill(0.f);
     if (beg < end) {
       gnf.load(Gf + v * (2 * D), lane);
       gdf.load(Gf + v * (2 * D) + D, lane);
@@ -404,6 +410,7 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
         const float gn = nv > 0.f ? geo : 0.f;
         f1[k] += gn;
         f2[k] = fmaf(gn, x.v[k], f2[k]);
+        sgn.v[k] += gn;
         acc.v[k] = fmaf(sg, gnb.v[k], acc.v[k]);
       }
     };
@@ -437,6 +444,9 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
       }
     }
     acc.store(gP + v * (5 * D) + 2 * D, lane);
+    // sum over in-edges of g_n: with the per-node sum of xhat from the forward, gB2h[v] = sum_i g_t_i follows
+    // without a pass over g_t (edge_bwd_src_kernel finishes it; edge_bwd_b_kernel overwrites it otherwise)
+    sgn.store(gP + v * (5 * D) + 4 * D, lane);
   }
   double s1[VPL], s2[VPL];
 #pragma unroll
@@ -502,15 +512,34 @@ edge_bwd_b_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
 
 // B5: per src node u over its out-edges i (u -> v):
 //   gB1h[u] = sum_i g_t_i -> gP[u, 3d:4d];   gA2h[u] = sum_i sigma_i * gnf[v_i] -> gP[u, d:2d]
+// With fix != 0 (batch norm, g_t produced inside the bwd-data GEMM): gP[u, 4d:5d] arrives holding
+// S = sum_{in(u)} g_n and is finished here as gB2h[u] = gamma rstd (S - indeg m1 - m2 sum_{in(u)} xhat).
 template <int D>
 __global__ void __launch_bounds__(kNodeThreads)
 edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ g_t,
-                    const float* __restrict__ e_out, const float* __restrict__ G, float* __restrict__ gP) {
+                    const float* __restrict__ e_out, const float* __restrict__ G, float* __restrict__ gP,
+                    int fix, int64_t E, const int32_t* __restrict__ in_ptr, const float* __restrict__ sum_xhat,
+                    const double* __restrict__ stats_e, const double* __restrict__ bstats_e,
+                    const float* __restrict__ gamma_e) {
   constexpr int VPL = D / 32;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * kNodeThreads) >> 5;
+  float fscale[VPL], fm1[VPL], fm2[VPL];
+  if (fix) {
+    const double inv_e = E > 0 ? 1.0 / (double)E : 0.0;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int c = Row<D>::channel(k, lane);
+      const double m = stats_e[c] * inv_e;
+      double var = stats_e[D + c] * inv_e - m * m;
+      var = var > 0.0 ? var : 0.0;
+      fscale[k] = __ldg(gamma_e + c) * (float)(1.0 / sqrt(var + (double)kNormEps));
+      fm1[k] = (float)(bstats_e[c] * inv_e);
+      fm2[k] = (float)(bstats_e[D + c] * inv_e);
+    }
+  }
   const float* Gf = G;
   for (int64_t u = gw; u < N; u += nw) {
     const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
@@ -545,6 +574,15 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
     }
     acc1.store(gP + u * (5 * D) + 3 * D, lane);
     acc2.store(gP + u * (5 * D) + D, lane);
+    if (fix) {
+      Row<D> sg, sx;
+      sg.load(gP + u * (5 * D) + 4 * D, lane);
+      sx.load(sum_xhat + u * D, lane);
+      const float indeg = (float)(__ldg(in_ptr + u + 1) - __ldg(in_ptr + u));
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) sg.v[k] = fscale[k] * (sg.v[k] - indeg * fm1[k] - fm2[k] * sx.v[k]);
+      sg.store(gP + u * (5 * D) + 4 * D, lane);
+    }
   }
 }
 

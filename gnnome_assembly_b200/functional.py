@@ -161,7 +161,7 @@ class _GatedGCNLayer(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         h_out, e_out = torch.empty(N, d, **f32), torch.empty(E, d, **f32)
         P, t, z = torch.empty(N, 5 * d, **f32), torch.empty(E, d, **f32), torch.empty(N, d, **f32)
-        agg = torch.empty(4, N, d, **f32)
+        agg = torch.empty(5, N, d, **f32)
         stats = torch.empty(4 * d, device=dev, dtype=torch.float64)
         check(_lib.lib().gg_layer_fwd(plan.handle, d, norm_kind, int(residual), ptr(h), ptr(e), ptr(Wn), ptr(bn),
                                       ptr(B3), ptr(b3), ptr(ge), ptr(be), ptr(gh), ptr(bh), ptr(h_out), ptr(e_out),
@@ -181,7 +181,7 @@ class _GatedGCNLayer(torch.autograd.Function):
         g_h = torch.zeros(N, d, **f32) if g_h is None else _cuda_f32(g_h)[0]
         g_e = None if g_e is None else _cuda_f32(g_e)[0]
         g_h_in, g_eo = torch.empty(N, d, **f32), torch.empty(E, d, **f32)
-        g_t = torch.empty(E, d, **f32)
+        g_t, g_e_in = torch.empty(E, d, **f32), torch.empty(E, d, **f32)
         gP, G = torch.empty(N, 5 * d, **f32), torch.empty(2, N, 2 * d, **f32)
         dWn, dbn = torch.empty(5 * d, d, **f32), torch.empty(5 * d, **f32)
         dB3, db3 = torch.empty(d, d, **f32), torch.empty(d, **f32)
@@ -190,10 +190,9 @@ class _GatedGCNLayer(torch.autograd.Function):
         check(_lib.lib().gg_layer_bwd(
             plan.handle, d, ctx.norm_kind, ctx.residual, ptr(h), ptr(e), ptr(e_out), ptr(Wn), ptr(B3), ptr(ge),
             ptr(be), ptr(gh), ptr(bh), ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), ptr(g_h), ptr(g_e),
-            ptr(g_h_in), ptr(g_eo), ptr(dWn), ptr(dbn), ptr(dB3), ptr(db3), ptr(dge), ptr(dbe), ptr(dgh), ptr(dbh),
+            ptr(g_h_in), ptr(g_e_in), ptr(dWn), ptr(dbn), ptr(dB3), ptr(db3), ptr(dge), ptr(dbe), ptr(dgh), ptr(dbh),
             ptr(gP), ptr(G), ptr(g_eo), ptr(g_t), ptr(bstats), _stream()), "gg_layer_bwd")
-        # g_e_in aliases g_eo (the bwd-data epilogue reads and writes the same element)
-        return None, None, None, g_h_in, g_eo, dWn, dbn, dB3, db3, dge, dbe, dgh, dbh
+        return None, None, None, g_h_in, g_e_in, dWn, dbn, dB3, db3, dge, dbe, dgh, dbh
 
 
 def gated_gcn_layer(plan, norm_kind, residual, h, e, Wn, bn, B3, b3, ge, be, gh, bh):

@@ -100,7 +100,7 @@ int gg_linear_bwd_weight(int64_t M, int N, int K, const float* dY, const float* 
  * bn[5d] their biases; B3[d,d], b3[d]; gamma/beta of bn_e and bn_h.
  * Outputs h_out[N,d], e_out[E,d].  Saved for backward / scratch (caller allocated):
  *   P[N,5d] projections, t[E,d] pre-norm edge gate, z[N,d] pre-norm node update,
- *   agg[4,N,d] = hf | hb | 1/(den_f+eps) | 1/(den_b+eps),
+ *   agg[5,N,d] = hf | hb | 1/(den_f+eps) | 1/(den_b+eps) | sum over in-edges of xhat_e (batch norm),
  *   stats[4d] doubles: sum_t | sum_t^2 | sum_z | sum_z^2 per channel (batch-norm only). */
 int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in,
                  const float* e_in, const float* Wn, const float* bn, const float* B3, const float* b3,
@@ -111,7 +111,9 @@ int gg_layer_fwd(const gg_plan_t* plan, int d, int norm_kind, int residual, cons
 /* Backward of the layer (the reference has no code for it: torch.autograd replays K16 of SURVEY §2b).
  * g_h[N,d], g_e[E,d]: gradients w.r.t. h_out / e_out (either may be NULL = zero).
  * Outputs: g_h_in[N,d], g_e_in[E,d], dWn[5d,d], dbn[5d], dB3[d,d], db3[d], dgamma/dbeta (4 x [d]).
- * Workspace: gP[N,5d], G[2,N,2d], g_eo[E,d], g_t[E,d], bstats[4d] doubles.  g_e_in may alias g_eo. */
+ * Workspace: gP[N,5d], G[2,N,2d], g_eo[E,d], g_t[E,d], bstats[4d] doubles.  Pass g_e_in distinct from g_eo:
+ * with batch norm on the tensor-core path g_t is then produced inside the g_e_in GEMM (no separate pass);
+ * an aliased g_e_in still works but takes the unfused path. */
 int gg_layer_bwd(const gg_plan_t* plan, int d, int norm_kind, int residual, const float* h_in,
                  const float* e_in, const float* e_out, const float* Wn, const float* B3,
                  const float* gamma_e, const float* beta_e, const float* gamma_h, const float* beta_h,
