@@ -38,7 +38,7 @@ constexpr int STAGES = 4;                         // (3 when the A operand is bu
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo   (+ a second A tile with an A transform)
 constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;  // 192 KB either way (4 x 48 KB or 3 x 64 KB)
-constexpr int COEF_BYTES = 7 * 256 * 4;           // A-transform coefficient vectors (7 x K floats, K <= 256)
+constexpr int COEF_BYTES = 6 * 256 * 4;           // A-transform coefficient vectors (6 x K floats, K <= 256)
 constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
 constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
 constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
@@ -218,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage0 = base;
   constexpr int OFF_STG = PIPE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
                 OFF_BAR = OFF_IDX + (Epi::kIdx ? IDX_BYTES : 0), OFF_COEF = OFF_BAR + BAR_BYTES;
-  float* coef = reinterpret_cast<float*>(gen + OFF_COEF);     // [7][K] per-channel coefficients (ATx only)
+  float* coef = reinterpret_cast<float*>(gen + OFF_COEF);     // [6][K]: mean, rstd, gamma, beta, m1, m2 (ATx only)
   float* staging = reinterpret_cast<float*>(gen + OFF_STG);
   double* sstat = reinterpret_cast<double*>(gen + OFF_STAT);
   int* sidx = reinterpret_cast<int*>(gen + OFF_IDX);
@@ -256,15 +256,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const double m = atx.stats[c] * atx.inv_count;
       double var = atx.stats[K + c] * atx.inv_count - m * m;
       var = var > 0.0 ? var : 0.0;
-      // xhat = t p0 + p1 ; n = xhat gamma + beta ; g_t = q0 g_n - q1 - xhat q2
-      const float rs = (float)(1.0 / sqrt(var + (double)kNormEps)), gm = __ldg(atx.gamma + c);
-      coef[0 * K + c] = rs;
-      coef[1 * K + c] = -(float)m * rs;
-      coef[2 * K + c] = gm;
+      coef[0 * K + c] = (float)m;
+      coef[1 * K + c] = (float)(1.0 / sqrt(var + (double)kNormEps));
+      coef[2 * K + c] = __ldg(atx.gamma + c);
       coef[3 * K + c] = __ldg(atx.beta + c);
-      coef[4 * K + c] = gm * rs;
-      coef[5 * K + c] = gm * rs * (float)(atx.bstats[c] * atx.inv_count);
-      coef[6 * K + c] = gm * rs * (float)(atx.bstats[K + c] * atx.inv_count);
+      coef[4 * K + c] = (float)(atx.bstats[c] * atx.inv_count);
+      coef[5 * K + c] = (float)(atx.bstats[K + c] * atx.inv_count);
     }
   }
   tc_fence_before();
@@ -360,37 +357,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_raw(s), ph);
         const uint8_t* st = gen + s * kStageBytes;
-        if constexpr (ATx::kActive) {
-          // ---- phase 1 (element-wise, layout agnostic): the A tile holds g_eo, the A2 tile holds t; rewrite the
-          // A tile in place as g_t.  float4 q = t + 128 i sits in row q / 8 at physical chunk t % 8, i.e. logical
-          // chunk (t % 8) ^ (row % 8) with row % 8 == (t / 8) % 8: the 4 channels of a thread are fixed, so
-          // its coefficients are 7 float4 per K-block.  g_t also goes to HBM (coalesced 128-byte row segments).
-          float4* pa = reinterpret_cast<float4*>(const_cast<uint8_t*>(st));
-          const float4* pt = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES);
-          const int K = (int)g.K;
-          const int ch0 = (int)(kbeg + (int64_t)kb * BK) + 4 * ((t & 7) ^ ((t >> 3) & 7));
-          const float4 p0 = *reinterpret_cast<const float4*>(coef + 0 * K + ch0);
-          const float4 p1 = *reinterpret_cast<const float4*>(coef + 1 * K + ch0);
-          const float4 gm = *reinterpret_cast<const float4*>(coef + 2 * K + ch0);
-          const float4 bt = *reinterpret_cast<const float4*>(coef + 3 * K + ch0);
-          const float4 q0 = *reinterpret_cast<const float4*>(coef + 4 * K + ch0);
-          const float4 q1 = *reinterpret_cast<const float4*>(coef + 5 * K + ch0);
-          const float4 q2 = *reinterpret_cast<const float4*>(coef + 6 * K + ch0);
-#pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            const int q = t + 128 * i;
-            const float4 ge = pa[q], tv = pt[q];
-            float4 o;
-            { const float xh = fmaf(tv.x, p0.x, p1.x); const float gn = fmaf(xh, gm.x, bt.x) > 0.f ? ge.x : 0.f; o.x = fmaf(q0.x, gn, -q1.x) - xh * q2.x; }
-            { const float xh = fmaf(tv.y, p0.y, p1.y); const float gn = fmaf(xh, gm.y, bt.y) > 0.f ? ge.y : 0.f; o.y = fmaf(q0.y, gn, -q1.y) - xh * q2.y; }
-            { const float xh = fmaf(tv.z, p0.z, p1.z); const float gn = fmaf(xh, gm.z, bt.z) > 0.f ? ge.z : 0.f; o.z = fmaf(q0.z, gn, -q1.z) - xh * q2.z; }
-            { const float xh = fmaf(tv.w, p0.w, p1.w); const float gn = fmaf(xh, gm.w, bt.w) > 0.f ? ge.w : 0.f; o.w = fmaf(q0.w, gn, -q1.w) - xh * q2.w; }
-            pa[q] = o;
-            const int64_t m = (int64_t)mt * BM + (q >> 3);
-            if (nt == 0 && m < g.M) *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + ch0) = o;
-          }
-          asm volatile("bar.sync 3, 128;" ::: "memory");   // rows are read back by other converter threads
-        }
         // ---- A row t of this K-block -> registers (k order), hi = raw bits, lo = x - trunc(x)
         uint32_t hi[32], lo[32];
         if constexpr (!A_MN) {
@@ -401,6 +367,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 x = row[c ^ (t & 7)];
             hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
             hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
+          }
+          if constexpr (ATx::kActive) {
+            // hi[] holds g_eo[row, c0 .. c0+31]; the second tile holds t: build g_t in place and store it
+            const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
+            const int K = (int)g.K;
+            const int c0 = (int)(kbeg + (int64_t)kb * BK);
+            const int64_t m = (int64_t)mt * BM + t;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 tv = row2[c ^ (t & 7)];
+              const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+              float gt[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ch = c0 + 4 * c + j;
+                const float rs = coef[1 * K + ch], gm = coef[2 * K + ch];
+                const float xh = (tt[j] - coef[0 * K + ch]) * rs;
+                const float nv = xh * gm + coef[3 * K + ch];
+                const float gn = nv > 0.f ? __uint_as_float(hi[4 * c + j]) : 0.f;
+                gt[j] = gm * rs * (gn - coef[4 * K + ch] - xh * coef[5 * K + ch]);
+                hi[4 * c + j] = __float_as_uint(gt[j]);
+              }
+              if (nt == 0 && m < g.M)
+                *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + c0 + 4 * c) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+            }
           }
         } else {
           // MN-major 128B_ATOM_32B tile: box t/32 (4 KB), k-row k at k*128 B, m' = t%32 lives in 32-byte chunk
