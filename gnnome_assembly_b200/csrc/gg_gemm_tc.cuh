@@ -38,7 +38,7 @@ constexpr int STAGES = 4;                         // (3 when the A operand is bu
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo   (+ a second A tile with an A transform)
 constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;  // 192 KB either way (4 x 48 KB or 3 x 64 KB)
-constexpr int COEF_BYTES = 6 * 256 * 4;           // A-transform coefficient vectors (6 x K floats, K <= 256)
+constexpr int COEF_BYTES = 8 * 256 * 4;           // A-transform coefficients: 2 float4 per channel, K <= 256 channels
 constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
 constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
 constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
@@ -218,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage0 = base;
   constexpr int OFF_STG = PIPE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
                 OFF_BAR = OFF_IDX + (Epi::kIdx ? IDX_BYTES : 0), OFF_COEF = OFF_BAR + BAR_BYTES;
-  float* coef = reinterpret_cast<float*>(gen + OFF_COEF);     // [6][K]: mean, rstd, gamma, beta, m1, m2 (ATx only)
+  float4* coef = reinterpret_cast<float4*>(gen + OFF_COEF);   // [K][2]: {p0, p1, gamma, beta}, {q0, q1, q2, -} (ATx only)
   float* staging = reinterpret_cast<float*>(gen + OFF_STG);
   double* sstat = reinterpret_cast<double*>(gen + OFF_STAT);
   int* sidx = reinterpret_cast<int*>(gen + OFF_IDX);
@@ -256,12 +256,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const double m = atx.stats[c] * atx.inv_count;
       double var = atx.stats[K + c] * atx.inv_count - m * m;
       var = var > 0.0 ? var : 0.0;
-      coef[0 * K + c] = (float)m;
-      coef[1 * K + c] = (float)(1.0 / sqrt(var + (double)kNormEps));
-      coef[2 * K + c] = __ldg(atx.gamma + c);
-      coef[3 * K + c] = __ldg(atx.beta + c);
-      coef[4 * K + c] = (float)(atx.bstats[c] * atx.inv_count);
-      coef[5 * K + c] = (float)(atx.bstats[K + c] * atx.inv_count);
+      // xhat = t p0 + p1 ; n = xhat gamma + beta ; g_t = q0 g_n - q1 - xhat q2
+      const float rs = (float)(1.0 / sqrt(var + (double)kNormEps)), gm = __ldg(atx.gamma + c);
+      coef[2 * c + 0] = make_float4(rs, -(float)m * rs, gm, __ldg(atx.beta + c));
+      coef[2 * c + 1] = make_float4(gm * rs, gm * rs * (float)(atx.bstats[c] * atx.inv_count),
+                                    gm * rs * (float)(atx.bstats[K + c] * atx.inv_count), 0.f);
     }
   }
   tc_fence_before();
@@ -371,7 +370,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (ATx::kActive) {
             // hi[] holds g_eo[row, c0 .. c0+31]; the second tile holds t: build g_t in place and store it
             const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
-            const int K = (int)g.K;
             const int c0 = (int)(kbeg + (int64_t)kb * BK);
             const int64_t m = (int64_t)mt * BM + t;
 #pragma unroll
@@ -382,11 +380,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int ch = c0 + 4 * c + j;
-                const float rs = coef[1 * K + ch], gm = coef[2 * K + ch];
-                const float xh = (tt[j] - coef[0 * K + ch]) * rs;
-                const float nv = xh * gm + coef[3 * K + ch];
-                const float gn = nv > 0.f ? __uint_as_float(hi[4 * c + j]) : 0.f;
-                gt[j] = gm * rs * (gn - coef[4 * K + ch] - xh * coef[5 * K + ch]);
+                const float4 ca = coef[2 * ch], cb = coef[2 * ch + 1];     // warp-uniform address: smem broadcast
+                const float xh = fmaf(tt[j], ca.x, ca.y);
+                const float gn = fmaf(xh, ca.z, ca.w) > 0.f ? __uint_as_float(hi[4 * c + j]) : 0.f;
+                gt[j] = fmaf(cb.x, gn, -cb.y) - xh * cb.z;
                 hi[4 * c + j] = __float_as_uint(gt[j]);
               }
               if (nt == 0 && m < g.M)
