@@ -206,7 +206,7 @@ def run_ours(args):
     E, N = g.num_edges, g.num_nodes
     torch.manual_seed(0)
     model = gg.GraphGatedGCNModel(1, 2, D, HID_E, L, HID_S, True, NB_PE).to(dev)
-    use_graph = (world == 1) and not args.no_cuda_graph
+    use_graph = not args.no_cuda_graph        # N > 1: the NCCL gradient all-reduce is captured with the step
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
     bucket = GradBucket(model.parameters()) if world > 1 else None
     # train.py:210-211: criterion = BCEWithLogitsLoss(pos_weight=tensor([1 / pos_to_neg_ratio], device=device))
@@ -237,7 +237,8 @@ def run_ours(args):
     if use_graph:
         from gnnome_assembly_b200.train_step import GraphedTrainStep
         n_before = _lib.launch_count()
-        graphed = GraphedTrainStep(model, opt, graph, d_e, d_pe, d_y, lambda s_, y_: bce_loss(s_, y_, POS_WEIGHT))
+        graphed = GraphedTrainStep(model, opt, graph, d_e, d_pe, d_y, lambda s_, y_: bce_loss(s_, y_, POS_WEIGHT),
+                                   after_backward=(lambda: bucket.allreduce_mean(active=True)) if bucket is not None else None)
         launches_per_step = (_lib.launch_count() - n_before) // 4      # 3 warm-up steps + 1 captured step
 
     def sync_all():

@@ -14,8 +14,11 @@ from .plan import plan_for
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, graph, e, pe, y, loss_fn, warmup=3):
+    def __init__(self, model, optimizer, graph, e, pe, y, loss_fn, warmup=3, after_backward=None):
+        """after_backward: optional hook between backward and optimizer.step, e.g. the data-parallel gradient
+        all-reduce (`dp.GradBucket.allreduce_mean`); NCCL collectives are captured with the step."""
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        self.after_backward = after_backward
         dev = pe.device
         self.graph = graph
         plan_for(graph, dev)                                   # built (and cached) outside the capture
@@ -36,6 +39,8 @@ class GraphedTrainStep:
         loss = self.loss_fn(scores, self.y)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
+        if self.after_backward is not None:
+            self.after_backward()
         self.optimizer.step()
         return loss.detach()
 
