@@ -307,9 +307,17 @@ def run_ours(args):
         t_dev, t_e2e, edges_total = float(tm[0]), float(tm[1]), float(t[2])
     else:
         edges_total = float(E)
-    if rank != 0:
+    def finish():
+        # A captured NCCL all-reduce keeps the communicator alive inside the CUDA graph; tearing the process
+        # group down with such graphs alive can block.  Everything is measured and printed by now: leave at once.
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peak, peak_src = peaks()
@@ -363,8 +371,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": cpu_val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
                                 "ms_per_step": cpu_dt * 1e3}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
