@@ -338,8 +338,18 @@ def run_ours(args):
     roofline = None
     if dom:
         r = kernels[dom]
+        # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (same workload)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic.json")
+        if os.path.exists(tpath):
+            key = {"gemm_edge_gate": "EpiEdgeGate", "gemm_bwd_e_in": "BnBwdATx", "gemm_dB3": "EpiAtomic"}.get(dom, dom)
+            for name, rec in json.load(open(tpath)).items():
+                if key in name and (E == 372650 and D == 128):
+                    traffic, traffic_src = rec["dram_bytes_per_launch"], "profiles/r1_ncu_dram_traffic.json (" + rec["report"] + ")"
+                    break
         roofline = {"kernel": dom, "bound": "hbm", "achieved": r["gbps"], "peak": peak, "unit": "GB/s",
-                    "frac": r["frac"], "traffic": None, "peak_source": peak_src, "share_of_step": r["share"],
+                    "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "share_of_step": r["share"],
                     "timing": "CUDA event pair per launch on the launching stream, 3 extra steps after the timed region",
                     "algorithmic_bytes_per_launch": ab[dom]}
     step_bytes = step_algorithmic_bytes(E, N, D, L)
