@@ -44,15 +44,16 @@ def _dev():
 def test_gpu_zscore_matches_reference(gold):
     dev = _dev()
     from gnnome_assembly_b200 import prep
-    e = prep.preprocess_features(torch.from_numpy(gold["overlap_length"]).to(dev), torch.from_numpy(gold["overlap_similarity"]).to(dev))
-    # bar: the reference computes (x - mean) / std in fp32.  For overlap_similarity (values in [0.99, 1], std
-    # 0.003) the fp32 mean carries a few ulps (~3e-7) of summation error which x - mean amplifies by 1/std to
-    # ~1e-4 in the z-score: that is noise of the reference, not signal.  The kernel does the subtraction and
-    # division in fp64 and rounds once, so it is held (a) to the exact fp64 value within fp32 rounding and
-    # (b) to the reference's values within that noise (column 0, overlap_length, mean/std ~ 1.6: 2e-5;
-    # column 1: 3e-4; absolute, |z| ~ 1).
+    # the golden generator hands overlap_length to the reference as int64 (as Raven's integer overlaps are,
+    # make_golden.py:78), which truncates the few fractional synthetic values: feed the same integers here
+    ol = np.trunc(gold["overlap_length"]).astype(np.float32)
+    e = prep.preprocess_features(torch.from_numpy(ol).to(dev), torch.from_numpy(gold["overlap_similarity"]).to(dev))
+    # bar: the reference computes (x - mean) / std in fp32; its fp32 mean carries a few ulps of summation error
+    # which x - mean turns into ~1e-5 absolute in the z-score (|z| ~ 1): noise of the reference, not signal.
+    # The kernel subtracts and divides in fp64 and rounds once, so it is held (a) to the exact fp64 value within
+    # fp32 rounding and (b) to the reference's values within that noise (2e-5 / 3e-4 absolute per column).
     ref64 = np.stack([(a - a.mean()) / a.std(ddof=1) for a in
-                      (gold["overlap_length"].astype(np.float64), gold["overlap_similarity"].astype(np.float64))], 1)
+                      (ol.astype(np.float64), gold["overlap_similarity"].astype(np.float64))], 1)
     assert np.abs(e.cpu().numpy() - ref64).max() < 5e-7
     assert torch.allclose(e.cpu()[:, 0], gold["e"][:, 0], rtol=0, atol=2e-5)
     assert torch.allclose(e.cpu()[:, 1], gold["e"][:, 1], rtol=0, atol=3e-4)
