@@ -37,6 +37,9 @@ SIGNATURES = {
     "gg_plan_out_ptr": (_p, [_p]),
     "gg_plan_out_eid": (_p, [_p]),
     "gg_plan_copy_array": (_i, [_p, _i, _p, _p]),
+    "gg_subplan_slab_words": (C.c_size_t, [_i64, _i64]),
+    "gg_subplan_count": (_i, [_p, _p, _i64, _p, C.POINTER(_i64)]),
+    "gg_subplan_fill": (_i, [_p, _p, _p, C.POINTER(_p)]),
     "gg_linear_fwd": (_i, [_i64, _i, _i, _p, _p, _p, _i, _p, _p]),
     "gg_linear_bwd_data": (_i, [_i64, _i, _i, _p, _p, _p, _p, _p, _p]),
     "gg_linear_bwd_weight": (_i, [_i64, _i, _i, _p, _p, _p, _p, _p]),

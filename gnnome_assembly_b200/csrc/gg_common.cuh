@@ -53,7 +53,16 @@ struct Plan {
   int32_t* node_perm = nullptr; // [N] internal node id -> caller node id
   int32_t* node_inv = nullptr;  // [N] caller node id -> internal node id
   int num_sms = 148;
+  // sub-graph plans (gg_subplan_fill): every array above lives in ONE caller-owned slab; plus the caller-facing view
+  int32_t* slab = nullptr;
+  int32_t* parent_eid = nullptr;  // [E] caller edge id -> parent caller edge id (dgl.EID)
+  int32_t* csrc = nullptr;        // [E] caller-order edge list in sub-graph node ids (sub_g.edges())
+  int32_t* cdst = nullptr;
+  void* sub_scratch = nullptr;    // SubScratch of a plan that has been used as a parent
 };
+
+struct SubScratch;
+void free_sub_scratch(SubScratch* s);
 
 constexpr float kAggEps = 1e-6f;   // gated_gcn_full.py:130,143
 constexpr float kNormEps = 1e-5f;  // nn.BatchNorm1d / nn.LayerNorm default eps

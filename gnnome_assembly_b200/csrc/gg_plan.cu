@@ -65,6 +65,8 @@ static bool is_device_ptr(const void* p) {
 
 static void free_plan(Plan* p) {
   if (!p) return;
+  free_sub_scratch(reinterpret_cast<SubScratch*>(p->sub_scratch));
+  if (p->slab) { delete p; return; }      // sub-graph plan: the arrays live in a caller-owned slab
   cudaFree(p->src); cudaFree(p->dst); cudaFree(p->in_ptr); cudaFree(p->out_ptr);
   cudaFree(p->out_eid); cudaFree(p->out_dst); cudaFree(p->perm); cudaFree(p->inv_perm);
   cudaFree(p->node_perm); cudaFree(p->node_inv);
@@ -266,10 +268,11 @@ GG_PLAN_GET(gg_plan_out_eid, out_eid, const int32_t*, nullptr)
 int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream) {
   GG_REQUIRE(plan && out, "plan_copy_array: null pointer");
   const Plan* p = reinterpret_cast<const Plan*>(plan);
-  const int32_t* srcs[9] = {p->perm, p->inv_perm, p->src, p->dst, p->in_ptr, p->out_ptr, p->out_eid,
-                            p->node_perm, p->node_inv};
-  GG_REQUIRE(which >= 0 && which < 9, "plan_copy_array: bad selector");
-  const int64_t n = (which == 4 || which == 5) ? p->N + 1 : (which >= 7 ? p->N : p->E);
+  const int32_t* srcs[12] = {p->perm, p->inv_perm, p->src, p->dst, p->in_ptr, p->out_ptr, p->out_eid,
+                             p->node_perm, p->node_inv, p->parent_eid, p->csrc, p->cdst};
+  GG_REQUIRE(which >= 0 && which < 12, "plan_copy_array: bad selector");
+  GG_REQUIRE(which < 9 || p->slab != nullptr, "plan_copy_array: selectors 9-11 exist on sub-graph plans only");
+  const int64_t n = (which == 4 || which == 5) ? p->N + 1 : ((which == 7 || which == 8) ? p->N : p->E);
   if (n > 0)
     GG_CUDA(cudaMemcpyAsync(out, srcs[which], n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return GG_OK;

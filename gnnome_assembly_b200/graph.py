@@ -25,6 +25,10 @@ class AssemblyGraph:
         return self._src.device
 
     def to(self, device):
+        device = torch.device(device)
+        tensors = [self._src, self._dst, *self.ndata.values(), *self.edata.values()]
+        if all(t.device == device or (t.is_cuda and device.type == "cuda" and device.index is None) for t in tensors):
+            return self                                   # already resident: keeps the cached GraphPlan attached
         g = AssemblyGraph(self._src.to(device), self._dst.to(device), self._n)
         g.ndata = {k: v.to(device) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device) for k, v in self.edata.items()}

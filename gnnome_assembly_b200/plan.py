@@ -8,11 +8,15 @@ re-sends the same graphs every epoch, train.py:239-245) and cached on a weak ref
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 
 import torch
 
 from . import _lib
+
+
+_SUBPLAN_LOCK = threading.Lock()
 
 
 class GraphPlan:
@@ -43,12 +47,47 @@ class GraphPlan:
         self._handle = handle
         self._finalizer = weakref.finalize(self, lib.gg_plan_destroy, handle)
 
+    @classmethod
+    def _adopt(cls, handle, device, relabel=True):
+        """Wrap a plan handle the library has just created (gg_subplan_fill)."""
+        lib = _lib.lib()
+        self = cls.__new__(cls)
+        self.device = torch.device(device)
+        self.num_nodes = int(lib.gg_plan_num_nodes(handle))
+        self.num_edges = int(lib.gg_plan_num_edges(handle))
+        self.relabel = bool(relabel)
+        self._handle = handle
+        self._finalizer = weakref.finalize(self, lib.gg_plan_destroy, handle)
+        return self
+
+    def subplan(self, nodes):
+        """Plan of the sub-graph induced by `nodes` (int64 CUDA tensor of this plan's caller node ids,
+        unique): sub-graph node j = nodes[j], edges in increasing parent edge id (DGL's g.subgraph(nodes)).
+        Built on the device by compaction of this plan (gg_subplan_count / gg_subplan_fill); extra arrays `parent_eid`
+        (dgl.EID), `csrc`, `cdst` (the sub-graph's own edge list)."""
+        nodes = torch.as_tensor(nodes)
+        if not nodes.is_cuda:
+            nodes = nodes.to(self.device)
+        nodes = nodes.to(torch.int64).contiguous()
+        lib = _lib.lib()
+        handle, n_edges = C.c_void_p(), C.c_int64()
+        with torch.cuda.device(self.device), _SUBPLAN_LOCK:
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.gg_subplan_count(self._handle, nodes.data_ptr(), nodes.numel(), stream, C.byref(n_edges)),
+                       "gg_subplan_count")
+            slab = torch.empty(lib.gg_subplan_slab_words(nodes.numel(), n_edges.value), dtype=torch.int32,
+                               device=self.device)
+            _lib.check(lib.gg_subplan_fill(self._handle, slab.data_ptr(), stream, C.byref(handle)), "gg_subplan_fill")
+        sub = GraphPlan._adopt(handle, self.device, self.relabel)
+        sub._slab = slab                                       # caller-owned backing store of the plan's arrays
+        return sub
+
     @property
     def handle(self):
         return self._handle
 
     _WHICH = {"perm": 0, "inv_perm": 1, "src": 2, "dst": 3, "in_ptr": 4, "out_ptr": 5, "out_eid": 6,
-              "node_perm": 7, "node_inv": 8}
+              "node_perm": 7, "node_inv": 8, "parent_eid": 9, "csrc": 10, "cdst": 11}
 
     def array(self, name):
         """Copy of one of the plan's device index arrays as an int32 torch tensor (cached)."""

@@ -76,8 +76,32 @@ const int32_t* gg_plan_out_ptr(const gg_plan_t* plan);
 const int32_t* gg_plan_out_eid(const gg_plan_t* plan);
 /* copy one of those arrays into a caller-owned device buffer (async on `stream`);
  * which: 0 perm, 1 inv_perm, 2 src, 3 dst, 4 in_ptr, 5 out_ptr, 6 out_eid, 7 node_perm[N] (internal ->
- * caller node id), 8 node_inv[N] */
+ * caller node id), 8 node_inv[N]; on plans made by gg_subplan_fill also 9 parent_eid[E] (sub-graph edge id
+ * -> parent edge id, DGL's edata[dgl.EID]), 10 / 11 the sub-graph's own edge list src[E] / dst[E] in
+ * sub-graph edge-id order and sub-graph node ids (what sub_g.edges() returns) */
 int gg_plan_copy_array(const gg_plan_t* plan, int which, int32_t* out, void* stream);
+
+/* ---- node-induced sub-graph plan (mini-batch path) ------------------------------------------------
+ * Replaces dgl.dataloading.ClusterGCNSampler.sample -> g.subgraph(node_ids) as the reference's mini-batch
+ * branch uses it (train.py:292-296 and :434-438; dgl.node_subgraph at inference.py:271) together with the
+ * plan the engine needs for the result.  nodes: DEVICE int64[n] parent node ids (the reference runs this
+ * branch on g.long(), train.py:290), unique; sub-graph node j is parent node nodes[j] and the sub-graph's
+ * edges are all parent edges with both ends selected, in increasing parent edge id (DGL's convention).
+ * Built entirely on the device as a stream compaction of the parent plan (4 exclusive scans + scatters,
+ * no sort): the selected nodes keep the parent's internal (breadth-first) order, so every edge array stays
+ * sorted and the gather locality of the parent carries over.
+ * Two steps, because the caller owns every buffer and the result's size is data dependent:
+ *   gg_subplan_count  marks the nodes and runs the scans into scratch owned by the parent plan, synchronises
+ *                     `stream` (one int has to reach the host) and returns the sub-graph's edge count;
+ *   gg_subplan_fill   scatters the result into `slab` (DEVICE int32[gg_subplan_slab_words(n, num_edges)],
+ *                     caller-owned and kept alive as long as the plan) and returns the plan.
+ * The pair must be issued on ONE stream, count then fill, with no other gg_subplan_* call on the same parent
+ * in between (the scratch belongs to the parent).  The result is an ordinary plan: every gg_layer_* /
+ * gg_score_* / gg_prep_* entry point and gg_subplan_* itself accept it; gg_plan_destroy releases the handle
+ * (not the slab). */
+size_t gg_subplan_slab_words(int64_t n, int64_t num_edges);
+int gg_subplan_count(const gg_plan_t* parent, const int64_t* nodes, int64_t n, void* stream, int64_t* num_edges);
+int gg_subplan_fill(const gg_plan_t* parent, int32_t* slab, void* stream, gg_plan_t** out);
 
 /* ---- dense linear ( nn.Linear ) -----------------------------------------------------------
  * Replaces torch.nn.functional.linear at models/full_graph.py:23-26 (linear_pe, linear1_edge,
