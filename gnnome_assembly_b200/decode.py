@@ -1,0 +1,196 @@
+"""Greedy contig decoding on the GPU — SURVEY.md §8f row 4; drop-in for inference.py:182-259 (`get_contigs`).
+
+    walks = get_contigs(g, succs, preds, edges, nb_paths, len_threshold, device)      # inference.py:369 / :487
+
+`g` needs what the reference reads: g.edata['score'], g.edata['prefix_length'], g.ndata['read_length'],
+g.edges(), g.num_nodes().  succs / preds / edges are the reference's pickled dictionaries
+(graph_parser.py:12-73); they may be None, in which case the adjacency is taken from g.edges() in edge-id
+order — which is how graph_parser builds the dictionaries in the first place.
+
+Per decoding iteration: sampling weights on the remaining graph (one kernel) -> nb_paths start edges (inverse
+CDF on the device; `start_edges=` pins them for reproducible runs and parity tests) -> ALL walks of the
+iteration concurrently, one warp each (`gg_decode_walks`) -> pick the walk reconstructing the longest sequence
+-> `gg_decode_commit` adds it, its strand mates and the jumped-over nodes to the visited bitmap.  One small D2H
+per iteration (lengths), one for the chosen walk.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_device(device, *tensors):
+    for t in tensors:
+        if torch.is_tensor(t) and t.is_cuda:
+            return t.device
+    d = torch.device(device) if device is not None else None
+    if d is not None and d.type == "cuda":
+        return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+    if not torch.cuda.is_available():
+        raise RuntimeError("gnnome_assembly_b200.decode: no CUDA device (the decoder has no CPU path)")
+    return torch.device("cuda", torch.cuda.current_device())     # inference.py passes device='cpu' to get_contigs
+
+
+class DecodeGraph:
+    """Successor / predecessor lists as device CSR in caller node ids, list order = the reference's."""
+
+    def __init__(self, src, dst, num_nodes, device, succs=None, preds=None, edges=None):
+        self.device = torch.device(device)
+        self.num_nodes = int(num_nodes)
+        src = torch.as_tensor(src).to(torch.int64).cpu().numpy()
+        dst = torch.as_tensor(dst).to(torch.int64).cpu().numpy()
+        self.num_edges = int(src.size)
+        if np.any(src == dst):
+            raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
+        # the reference looks edges up through a {(src, dst): id} dictionary (graph_parser.py:69-72): of parallel
+        # edges only the LAST id is ever seen — scores and prefix lengths are read through that id
+        key = src * max(self.num_nodes, 1) + dst
+        _, inv = np.unique(key, return_inverse=True)
+        last = np.full(inv.max() + 1 if inv.size else 0, -1, dtype=np.int64)
+        np.maximum.at(last, inv, np.arange(src.size))
+        canon = last[inv] if inv.size else np.zeros(0, dtype=np.int64)
+        if succs is None or preds is None:
+            # graph_parser.py:27-29, :48-50: lists are filled by one pass over graph.edges() in edge-id order
+            s_ord = np.argsort(src, kind="stable")
+            p_ord = np.argsort(dst, kind="stable")
+            s_node, p_node = dst[s_ord], src[p_ord]
+            s_eid, p_eid = canon[s_ord], canon[p_ord]
+            s_ptr = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=self.num_nodes))])
+            p_ptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=self.num_nodes))])
+        else:
+            s_ptr, s_node, s_eid = self._from_dict(succs, edges, forward=True)
+            p_ptr, p_node, p_eid = self._from_dict(preds, edges, forward=False)
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+        self.succ_ptr, self.succ_node, self.succ_eid = i32(s_ptr), i32(s_node), i32(s_eid)
+        self.pred_ptr, self.pred_node, self.pred_eid = i32(p_ptr), i32(p_node), i32(p_eid)
+        self.src, self.dst, self.canon_eid = i32(src), i32(dst), i32(canon)
+        self._edge_of = None
+        self._src_np, self._dst_np = src, dst
+
+    def _from_dict(self, adj, edges, forward):
+        if edges is None:
+            raise ValueError("decode: succs / preds given without the edges dictionary")
+        ptr_, node, eid = [0], [], []
+        for u in range(self.num_nodes):
+            for v in adj.get(u, ()):
+                node.append(v)
+                eid.append(edges[(u, v)] if forward else edges[(v, u)])
+            ptr_.append(len(node))
+        return np.array(ptr_), np.array(node, dtype=np.int64), np.array(eid, dtype=np.int64)
+
+    def edge_id(self, s, d):
+        if self._edge_of is None:
+            self._edge_of = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(self._src_np, self._dst_np))}
+        return self._edge_of[(int(s), int(d))]
+
+
+class WalkBatch:
+    """Result of one decode_walks call (device tensors; `.host()` brings the small ones over in one go)."""
+
+    def __init__(self, N, n_walks, device):
+        words = (N + 31) // 32
+        self.N, self.n, self.words = N, n_walks, words
+        self.local_visited = torch.empty(max(n_walks, 1) * words, dtype=torch.int32, device=device)
+        self.walk_buf = torch.empty(max(n_walks, 1) * 2 * N, dtype=torch.int32, device=device)
+        self.meta = torch.zeros(2 * max(n_walks, 1) + 2, dtype=torch.int32, device=device)   # beg | len | err
+        self.seq_len = torch.zeros(max(n_walks, 1), dtype=torch.int64, device=device)
+
+    def host(self):
+        meta = self.meta.cpu()
+        n = self.n
+        return meta[:n].numpy(), meta[n:2 * n].numpy(), self.seq_len.cpu().numpy()[:n], int(meta[2 * max(n, 1)])
+
+    def walk(self, w, beg, length):
+        return self.walk_buf[w * 2 * self.N + beg: w * 2 * self.N + beg + length]
+
+
+def decode_walks(dg, scores, prefix_length, read_length, visited, start_src, start_dst, start_eid, out=None):
+    """All walks of one iteration (inference.py:236-241 for every sampled edge).  Inputs are device tensors:
+    scores fp32[E], prefix_length int64[E], read_length int64[N], visited int32[(N+31)//32] (bitmap),
+    start_* int32[n_walks].  Returns a WalkBatch."""
+    n = int(start_src.numel())
+    wb = out if out is not None and out.n == n else WalkBatch(dg.num_nodes, n, dg.device)
+    m = wb.meta
+    check(_lib.lib().gg_decode_walks(
+        dg.num_nodes, ptr(dg.succ_ptr), ptr(dg.succ_node), ptr(dg.succ_eid), ptr(dg.pred_ptr), ptr(dg.pred_node),
+        ptr(dg.pred_eid), ptr(scores), ptr(prefix_length), ptr(read_length), ptr(visited), n,
+        ptr(start_src), ptr(start_dst), ptr(start_eid), ptr(wb.local_visited), ptr(wb.walk_buf),
+        m.data_ptr(), m.data_ptr() + 4 * n, ptr(wb.seq_len), m.data_ptr() + 4 * 2 * max(n, 1), _stream()),
+        "gg_decode_walks")
+    return wb
+
+
+def commit_walk(dg, wb, w, beg, length, visited):
+    """inference.py:223-234,241: the chosen walk, its strand mates and the jumped-over nodes become visited."""
+    walk = wb.walk(w, beg, length)
+    loc = wb.local_visited[w * wb.words:(w + 1) * wb.words]
+    check(_lib.lib().gg_decode_commit(dg.num_nodes, ptr(dg.succ_ptr), ptr(dg.succ_node), ptr(dg.pred_ptr),
+                                      ptr(dg.pred_node), ptr(walk), int(length), ptr(loc), ptr(visited), _stream()),
+          "gg_decode_commit")
+
+
+def sample_edges(dg, scores, visited, nb_paths, generator=None):
+    """inference.py:279-286 on the graph without the visited nodes (:262-275): indices of nb_paths edges drawn
+    with probability proportional to max(sigmoid(score), 1e-9).  None if no edge is left."""
+    w = torch.empty(dg.num_edges, dtype=torch.float32, device=dg.device)
+    check(_lib.lib().gg_decode_edge_weights(dg.num_edges, ptr(dg.src), ptr(dg.dst), ptr(scores), ptr(visited), ptr(w),
+                                            _stream()), "gg_decode_edge_weights")
+    cdf = torch.cumsum(w.double(), 0)
+    total = float(cdf[-1]) if dg.num_edges else 0.0
+    if total <= 0.0:
+        return None
+    u = torch.rand(nb_paths, dtype=torch.float64, device=dg.device, generator=generator) * total
+    return torch.searchsorted(cdf, u, right=True).clamp_(max=dg.num_edges - 1)
+
+
+def get_contigs(g, succs, preds, edges, nb_paths=50, len_threshold=20, device="cpu", start_edges=None, scores=None,
+                generator=None):
+    """Drop-in for inference.py:182-259.  Returns the list of contigs, each a list of node ids.
+    start_edges: optional iterable of per-iteration (src_ids, dst_ids) sequences replacing the random draw.
+    scores: optional per-edge tensor to walk on instead of g.edata['score'] (the overlap-length / similarity
+    baselines of get_contigs_baselines, inference.py:134-141)."""
+    score_t = g.edata["score"] if scores is None else scores
+    dev = _cuda_device(device, score_t)
+    src, dst = g.edges()
+    N = int(g.num_nodes())
+    dg = DecodeGraph(src, dst, N, dev, succs, preds, edges)
+    with torch.cuda.device(dev):
+        score_d = torch.as_tensor(score_t).reshape(-1).to(dev, torch.float32).contiguous()
+        prefix = torch.as_tensor(g.edata["prefix_length"]).reshape(-1).to(dev, torch.int64).contiguous()
+        rlen = torch.as_tensor(g.ndata["read_length"]).reshape(-1).to(dev, torch.int64).contiguous()
+        visited = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
+        starts = iter(start_edges) if start_edges is not None else None
+        all_contigs, wb = [], None
+        while True:
+            if starts is not None:
+                try:
+                    s_list, d_list = next(starts)
+                except StopIteration:
+                    break
+                eid = torch.tensor([dg.edge_id(a, b) for a, b in zip(s_list, d_list)], dtype=torch.int32, device=dev)
+                s_t = torch.as_tensor(np.asarray(s_list), dtype=torch.int32).to(dev)
+                d_t = torch.as_tensor(np.asarray(d_list), dtype=torch.int32).to(dev)
+            else:
+                idx = sample_edges(dg, score_d, visited, nb_paths, generator)
+                if idx is None:
+                    break
+                eid = dg.canon_eid[idx]
+                s_t, d_t = dg.src[idx], dg.dst[idx]
+            wb = decode_walks(dg, score_d, prefix, rlen, visited, s_t, d_t, eid, out=wb)
+            beg, length, seq_len, err = wb.host()
+            if err:
+                raise RuntimeError("decode: a greedy walk ran into a cycle of single-neighbour nodes "
+                                   "(the reference's walk_forwards / walk_backwards would not terminate)")
+            best = int(np.argmax(seq_len))                         # max(all_walks, key=get_contig_length): first maximum
+            if int(length[best]) < len_threshold:                  # inference.py:243-244
+                break
+            all_contigs.append(wb.walk(best, int(beg[best]), int(length[best])).cpu().tolist())
+            commit_walk(dg, wb, best, int(beg[best]), int(length[best]), visited)
+    return all_contigs

@@ -30,6 +30,8 @@ class SynthGraph:
     y: np.ndarray            # float32 [E]    1 = true overlap
     overlap_length: np.ndarray
     overlap_similarity: np.ndarray
+    read_length: np.ndarray = None      # int64 [N]  ndata['read_length']  (graph_parser.py:256,284)
+    prefix_length: np.ndarray = None    # int64 [E]  edata['prefix_length'] = read_length[src] - overlap_length (:280-281)
 
     @property
     def num_edges(self):
@@ -78,6 +80,7 @@ def make_assembly_graph(chrom="chr19", seed=0, genome_len=None, target_edges=Non
     keep = ends > run_max
     starts, ends = starts[keep], ends[keep]
     R = len(starts)
+    read_len_r = (ends - starts).astype(np.int64)
     # + strand overlaps i -> j iff start_i < start_j < end_i - min_overlap
     lo = np.searchsorted(starts, starts, side="right")
     hi = np.searchsorted(starts, ends - min_overlap, side="left")
@@ -117,8 +120,12 @@ def make_assembly_graph(chrom="chr19", seed=0, genome_len=None, target_edges=Non
     out_deg = np.bincount(src, minlength=N).astype(np.float32)
     pr = pagerank_pe(src, dst, N, pe_dim) if pe_dim > 0 else np.zeros((N, 0), np.float32)   # pe_dim=0: structure only
     pe = np.concatenate([in_deg[:, None], out_deg[:, None], pr], axis=1)
+    read_length = np.empty(N, dtype=np.int64)
+    read_length[2 * relabel] = read_len_r
+    read_length[2 * relabel + 1] = read_len_r
+    prefix_length = np.maximum(read_length[src] - ol.astype(np.int64), 1)
     return SynthGraph(src.astype(np.int32), dst.astype(np.int32), N, e, pe.astype(np.float32), y,
-                      ol.astype(np.float32), sim.astype(np.float32))
+                      ol.astype(np.float32), sim.astype(np.float32), read_length, prefix_length)
 
 
 def make_random_graph(num_nodes, num_edges, seed=0, pe_dim=16, isolated_frac=0.0) -> SynthGraph:

@@ -184,6 +184,42 @@ int gg_bce_bwd(int64_t E, const float* scores, const float* y, float pos_weight,
  * caller's edge-id order (the contract at the model boundary) and the internal order. */
 int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx, float* out, void* stream);
 
+/* ---- greedy contig decoding -------------------------------------------------------------------
+ * Replaces the body of get_contigs (inference.py:182-259): per decoding iteration the reference samples
+ * nb_paths start edges and runs walk_forwards / walk_backwards (inference.py:31-77) for each of them one after
+ * the other in Python.  Here all walks of an iteration run concurrently, one warp per walk.
+ * Adjacency is given in CALLER node ids (the reference's succs / preds dictionaries flattened to CSR, list
+ * order kept: ties in the arg-max and the single-neighbour shortcut depend on it): *_ptr int32[N+1], *_node
+ * int32[E], *_eid int32[E] = id of the edge (current -> neighbour) for successors, (neighbour -> current) for
+ * predecessors (the reference's `edges` dictionary).  Node 2k and 2k+1 are the two strands of one read
+ * (`current ^ 1`, inference.py:39).  The graph must have no self loops (the reference drops them, :187).
+ * scores float32[E] (edata['score'], or overlap_length / overlap_similarity for the baselines :134-141),
+ * prefix_length int64[E], read_length int64[N] (get_contig_length, inference.py:20-28), all by caller ids.
+ * visited: uint32[(N+31)/32] bitmap of the nodes of finished contigs.
+ *
+ * gg_decode_walks: for walk w, forward from start_dst[w] then backward from start_src[w] (with the forward
+ * walk's nodes masked, :238); writes the node sequence to walk_buf[w*2N + out_beg[w] .. + out_len[w]), the
+ * walk's own visited set (its nodes and their strand mates) to local_visited[w*words ..], and the length of
+ * the reconstructed sequence to out_seq_len[w].  *err (device int) is set to 1 if a walk ran into a cycle of
+ * single-neighbour nodes (the reference never returns in that case; the walk is cut at N nodes).
+ * Buffers (caller-owned, device): local_visited uint32[n_walks*words], walk_buf int32[n_walks*2N]. */
+int gg_decode_walks(int64_t N, const int32_t* succ_ptr, const int32_t* succ_node, const int32_t* succ_eid,
+                    const int32_t* pred_ptr, const int32_t* pred_node, const int32_t* pred_eid, const float* scores,
+                    const int64_t* prefix_length, const int64_t* read_length, const uint32_t* visited, int n_walks,
+                    const int32_t* start_src, const int32_t* start_dst, const int32_t* start_eid,
+                    uint32_t* local_visited, int32_t* walk_buf, int32_t* out_beg, int32_t* out_len,
+                    int64_t* out_seq_len, int* err, void* stream);
+/* gg_decode_commit: inference.py:223-234,241 for the chosen walk: visited |= walk_visited | {t, t^1 : t in
+ * succs[ss] & preds[dd] for consecutive walk nodes ss, dd}.  walk: device int32[len]. */
+int gg_decode_commit(int64_t N, const int32_t* succ_ptr, const int32_t* succ_node, const int32_t* pred_ptr,
+                     const int32_t* pred_node, const int32_t* walk, int len, const uint32_t* walk_visited,
+                     uint32_t* visited, void* stream);
+/* gg_decode_edge_weights: the (unnormalised) sampling weights of sample_edges (inference.py:279-286) on the
+ * graph without the visited nodes (get_subgraph, :262-275): max(sigmoid(score), 1e-9) for an edge whose two
+ * ends are unvisited and distinct, 0 otherwise.  src/dst int32[E] in edge-id order. */
+int gg_decode_edge_weights(int64_t E, const int32_t* src, const int32_t* dst, const float* scores,
+                           const uint32_t* visited, float* weights, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ semantics, exactly the API surface those files touch:
   g.update_all(fn.u_mul_e(a, e, m), fn.sum(m, o)) gated_gcn_full.py:128,141   zero in-degree -> 0
   g.update_all(fn.copy_e(e, m), fn.sum(m, o))     gated_gcn_full.py:129,142
   g.local_scope(), g.ndata, g.edata, g.edges()    score_predictor.py:21-25
+  dgl.remove_self_loop, dgl.node_subgraph(store_ids=True), dgl.NID   inference.py:187,271-273 (decoder golden vectors)
 
 `install()` registers it as `dgl` / `dgl.function` in sys.modules.  Used by
 tests/golden/make_golden.py in the build container only; never on the product path.
@@ -76,6 +77,12 @@ class DGLGraph:
     def int(self):                                       # utils.py:68
         return self
 
+    def to(self, device):                                # inference.py:188 (CPU only here)
+        return self
+
+    def nodes(self):                                     # graph_parser.py:26
+        return torch.arange(self._n)
+
     def in_degrees(self):                                # utils.py:102
         return torch.bincount(self._dst, minlength=self._n)
 
@@ -134,11 +141,37 @@ def reverse(g, copy_ndata=True, copy_edata=False):
     return r
 
 
+NID = EID = "_ID"
+
+
+def remove_self_loop(g):                                 # inference.py:187
+    keep = g._src != g._dst
+    r = DGLGraph(g._src[keep], g._dst[keep], g._n)
+    r.ndata = dict(g.ndata)
+    r.edata = {k: v[keep] for k, v in g.edata.items()}
+    return r
+
+
+def node_subgraph(g, nodes, store_ids=True):             # inference.py:271: node j of the result = nodes[j],
+    nodes = torch.as_tensor(nodes).long()                # edges = induced edges in parent edge-id order
+    local = torch.full((g._n,), -1, dtype=torch.int64)
+    local[nodes] = torch.arange(nodes.numel())
+    keep = (local[g._src] >= 0) & (local[g._dst] >= 0)
+    r = DGLGraph(local[g._src[keep]], local[g._dst[keep]], nodes.numel())
+    r.ndata = {k: v[nodes] for k, v in g.ndata.items()}
+    r.edata = {k: v[keep] for k, v in g.edata.items()}
+    if store_ids:
+        r.ndata[NID] = nodes
+        r.edata[EID] = torch.nonzero(keep).squeeze(1)
+    return r
+
+
 def install():
     """Register this module as `dgl` and `dgl.function` (call before importing reference code)."""
     me = sys.modules[__name__]
     dgl = types.ModuleType("dgl")
     dgl.DGLGraph, dgl.graph, dgl.reverse = DGLGraph, graph, reverse
+    dgl.remove_self_loop, dgl.node_subgraph, dgl.NID, dgl.EID = remove_self_loop, node_subgraph, NID, EID
     dgl.function = me
     sys.modules["dgl"] = dgl
     sys.modules["dgl.function"] = me
