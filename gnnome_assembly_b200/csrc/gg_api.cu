@@ -18,10 +18,19 @@ static int sm_count() {
   return n;
 }
 
-// one warp per node, 8 warps per CTA, at most 8 CTAs resident per SM (grid-stride beyond that)
-static unsigned node_grid(int64_t n) {
+// one warp per node, 8 warps per CTA, grid-stride over the nodes.  The grid is exactly ONE wave: as many CTAs as
+// are resident at once for this kernel's register use (occupancy API, cached per kernel) x the SM count -- a
+// grid of 8 CTAs per SM ran as 2.7 waves of 3 resident CTAs, the last one a third empty.
+template <class Kern>
+static unsigned node_grid(Kern kern, int64_t n) {
+  static int per_sm = 0;                      // one static per kernel instantiation
+  if (per_sm == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kNodeThreads, 0) != cudaSuccess || occ < 1) occ = 2;
+    per_sm = occ;
+  }
   int64_t blocks = (n + (kNodeThreads / 32) - 1) / (kNodeThreads / 32);
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -125,15 +134,15 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     if (rc) return rc;
   }
   GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
-  edge_gate_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+  edge_gate_fwd_kernel<D, NORM><<<node_grid(edge_gate_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
       N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
   GG_KERNEL_END("edge_gate_fwd_kernel", st);
   GG_KERNEL_BEGIN("node_agg_fwd_kernel", st);
-  node_agg_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+  node_agg_fwd_kernel<D, NORM><<<node_grid(node_agg_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
       N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D);
   GG_KERNEL_END("node_agg_fwd_kernel", st);
   GG_KERNEL_BEGIN("node_update_fwd_kernel", st);
-  node_update_fwd_kernel<D, NORM><<<node_grid(N), kNodeThreads, 0, st>>>(
+  node_update_fwd_kernel<D, NORM><<<node_grid(node_update_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
       N, z, h_in, stats + 2 * D, gamma_h, beta_h, residual, h_out);
   GG_KERNEL_END("node_update_fwd_kernel", st);
   return GG_OK;
@@ -149,16 +158,15 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
                           float* gP, float* G, float* g_eo, float* g_t, double* bstats, cudaStream_t st) {
   const int64_t N = pl->N, E = pl->E;
   GG_CUDA(cudaMemsetAsync(bstats, 0, sizeof(double) * 4 * D, st));
-  const unsigned grid = node_grid(N);
   GG_KERNEL_BEGIN("node_bwd_reduce_kernel", st);
-  node_bwd_reduce_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, gamma_h, beta_h, bstats);
+  node_bwd_reduce_kernel<D, NORM><<<node_grid(node_bwd_reduce_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, gamma_h, beta_h, bstats);
   GG_KERNEL_END("node_bwd_reduce_kernel", st);
   GG_KERNEL_BEGIN("node_bwd_apply_kernel", st);
-  node_bwd_apply_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, bstats, gamma_h, beta_h,
+  node_bwd_apply_kernel<D, NORM><<<node_grid(node_bwd_apply_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, bstats, gamma_h, beta_h,
                                                                agg, gP, G);
   GG_KERNEL_END("node_bwd_apply_kernel", st);
   GG_KERNEL_BEGIN("edge_bwd_a_kernel", st);
-  edge_bwd_a_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
+  edge_bwd_a_kernel<D, NORM><<<node_grid(edge_bwd_a_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
                                                            gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D);
   GG_KERNEL_END("edge_bwd_a_kernel", st);
   int rc;
@@ -175,12 +183,12 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
     if (rc) return rc;
   } else {
     GG_KERNEL_BEGIN("edge_bwd_b_kernel", st);
-    edge_bwd_b_kernel<D, NORM><<<grid, kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
+    edge_bwd_b_kernel<D, NORM><<<node_grid(edge_bwd_b_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, E, pl->in_ptr, t, g_eo, stats, bstats + 2 * D,
                                                              gamma_e, beta_e, g_t, gP);
     GG_KERNEL_END("edge_bwd_b_kernel", st);
   }
   GG_KERNEL_BEGIN("edge_bwd_src_kernel", st);
-  edge_bwd_src_kernel<D><<<grid, kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP,
+  edge_bwd_src_kernel<D><<<node_grid(edge_bwd_src_kernel<D>, N), kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP,
                                                        fused_gt ? 1 : 0, E, pl->in_ptr, agg + 4 * N * D, stats,
                                                        bstats + 2 * D, gamma_e);
   GG_KERNEL_END("edge_bwd_src_kernel", st);
@@ -411,7 +419,7 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
   rc = linear_bwd_weight("gemm_score_dW1e", E, H, d, g_pre, H, e, d, dW1e, nullptr, st);                      // dW1e = g_pre^T e
   if (rc) return rc;
   GG_KERNEL_BEGIN("edge_to_node_sums_kernel", st);
-  edge_to_node_sums_kernel<64><<<node_grid(N), kNodeThreads, 0, st>>>(N, pl->in_ptr, pl->out_ptr, pl->out_eid, g_pre, gQ);
+  edge_to_node_sums_kernel<64><<<node_grid(edge_to_node_sums_kernel<64>, N), kNodeThreads, 0, st>>>(N, pl->in_ptr, pl->out_ptr, pl->out_eid, g_pre, gQ);
   GG_KERNEL_END("edge_to_node_sums_kernel", st);
   rc = linear_bwd_data("gemm_score_bwd_x", N, 2 * H, d, gQ, 2 * H, Wq, d, nullptr, nullptr, g_x, d, st);    // g_x = gQ Wq
   if (rc) return rc;

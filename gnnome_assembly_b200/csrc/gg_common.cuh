@@ -55,6 +55,7 @@ struct Plan {
   int num_sms = 148;
   // sub-graph plans (gg_subplan_fill): every array above lives in ONE caller-owned slab; plus the caller-facing view
   int32_t* slab = nullptr;
+  int32_t* host_slab = nullptr;   // gg_plan_create: the library-owned allocation behind all arrays
   int32_t* parent_eid = nullptr;  // [E] caller edge id -> parent caller edge id (dgl.EID)
   int32_t* csrc = nullptr;        // [E] caller-order edge list in sub-graph node ids (sub_g.edges())
   int32_t* cdst = nullptr;

@@ -49,7 +49,9 @@ constexpr int smem_bytes() {
   return 1024 /*align slack*/ + PIPE_BYTES + STAGING_BYTES + (kStats ? STATS_BYTES : 0) + (Epi::kIdx ? IDX_BYTES : 0) +
          BAR_BYTES + (ATx::kActive ? COEF_BYTES : 0);
 }
-constexpr int THREADS = 512;
+constexpr int THREADS = 512;                      // 4 control + 4 converter + 8 epilogue warps
+constexpr int THREADS_ATX = 640;                  // an A transform doubles the converter: 4 + 8 + 8 warps
+template <class ATx> constexpr int threads() { return ATx::kActive ? THREADS_ATX : THREADS; }
 constexpr int TMEM_COLS = 512;                    // 2 x 128 accumulator columns + 4 stages x (32 hi + 32 lo) A columns
 constexpr int TMEM_A0 = 256;
 
@@ -118,6 +120,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -206,12 +216,19 @@ struct BnBwdATx {
 
 // ---------------------------------------------------------------------------------- the kernel
 template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(threads<ATx>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, Args g, Epi epi, ATx atx) {
   static_assert(!ATx::kActive || !A_MN, "A transforms are written for K-major A");
   constexpr int kStages = ATx::kActive ? 3 : 4;
   constexpr int kStageBytes = (ATx::kActive ? 4 : 3) * TILE_BYTES;
+  // warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle | converters | 8 epilogue warps.
+  // With an A transform the converter is the longest stage of the pipeline (ncu: its warps never wait), so it
+  // gets 8 warps: warps w and w + 4 share a TMEM lane quarter and each takes 16 of the K-block's 32 columns.
+  constexpr int kConvWarps = ATx::kActive ? 8 : 4;
+  constexpr int kConvThreads = 32 * kConvWarps;
+  constexpr int kEpiWarp0 = 4 + kConvWarps;          // multiple of 4: epilogue warp w reads TMEM lanes 32 (w % 4) ..
+  constexpr int kEpiThread0 = 32 * kEpiWarp0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -232,12 +249,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // register split (setmaxnreg): a fused epilogue that holds a whole tile of prefetched operands gets more
   constexpr bool kHeavyEpi = (sizeof(typename Epi::PreD) + sizeof(typename Epi::PreN)) >= 32;
-  constexpr int kCtrlRegs = kHeavyEpi ? 24 : 40, kConvRegs = kHeavyEpi ? 96 : 104, kEpiRegs = kHeavyEpi ? 192 : 184;
+  constexpr int kCtrlRegs = ATx::kActive ? 24 : (kHeavyEpi ? 24 : 40), kConvRegs = ATx::kActive ? 72 : (kHeavyEpi ? 96 : 104),
+                kEpiRegs = ATx::kActive ? 152 : (kHeavyEpi ? 192 : 184);
+  // setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x launch registers), not the
+  // whole register file: 640 x 96 = 61440 >= 128 x 24 + 256 x 72 + 256 x 152; 512 x 128 = 65536 >= 128 x 24 + 128 x 96 + 256 x 192
+  static_assert(128 * kCtrlRegs + kConvThreads * kConvRegs + 256 * kEpiRegs <= (ATx::kActive ? 640 * 96 : 512 * 128),
+                "setmaxnreg split exceeds the CTA's register pool: setmaxnreg.inc would block forever");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), 128); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), kConvThreads); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -246,13 +268,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if constexpr (kStats) {
-    if (warp >= 8) {
-      for (int i = threadIdx.x - 256; i < 4 * BN * 2; i += 256) sstat[i] = 0.0;
+    if (warp >= kEpiWarp0) {
+      for (int i = threadIdx.x - kEpiThread0; i < 4 * BN * 2; i += 256) sstat[i] = 0.0;
     }
   }
   if constexpr (ATx::kActive) {
     const int K = (int)g.K;
-    for (int c = threadIdx.x; c < K; c += THREADS) {
+    for (int c = threadIdx.x; c < K; c += (int)blockDim.x) {
       const double m = atx.stats[c] * atx.inv_count;
       double var = atx.stats[K + c] * atx.inv_count - m * m;
       var = var > 0.0 ? var : 0.0;
@@ -343,7 +365,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
-  } else if (warp < 8) {
+  } else if (ATx::kActive && warp < kEpiWarp0) {
+    // ================================================================ converter with an A transform
+    // 256 threads: thread = (A row t, half of the K-block's 32 columns)
+    reg_dec<kConvRegs>();
+    if constexpr (ATx::kActive) {
+      const int ct = threadIdx.x - 128;
+      const int cw = ct >> 5;
+      const int t = 32 * (cw & 3) + lane;
+      const int half = cw >> 2;
+      const uint32_t lane_base = (uint32_t)(32 * (cw & 3)) << 16;
+      int s = 0; uint32_t ph = 0;
+      for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int mt, nt, sp; decode(w, mt, nt, sp);
+        int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+        const int64_t m = (int64_t)mt * BM + t;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_raw(s), ph);
+          const uint8_t* st = gen + s * kStageBytes;
+          // g_eo[row, c0 + 16 half ..+15] (tile 0) and t (tile 3) -> g_t (stored, and the A operand)
+          const float4* row = reinterpret_cast<const float4*>(st + t * 128);
+          const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
+          const int c0 = (int)(kbeg + (int64_t)kb * BK);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cc = 4 * half + c;                                // logical 16-byte chunk of the 128-byte row
+            const float4 gv = row[cc ^ (t & 7)];
+            const float4 tv = row2[cc ^ (t & 7)];
+            const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+            float gt[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ch = c0 + 4 * cc + j;
+              const float4 ca = coef[2 * ch], cb = coef[2 * ch + 1];     // warp-uniform address: smem broadcast
+              const float xh = fmaf(tt[j], ca.x, ca.y);
+              const float gn = fmaf(xh, ca.z, ca.w) > 0.f ? ge[j] : 0.f;
+              gt[j] = fmaf(cb.x, gn, -cb.y) - xh * cb.z;
+              hi[4 * c + j] = __float_as_uint(gt[j]);
+            }
+            if (nt == 0 && m < g.M)
+              *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + c0 + 4 * cc) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float x = __uint_as_float(hi[k]);
+            lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
+          }
+          const uint32_t ta = tmem_base + lane_base + (uint32_t)(TMEM_A0 + 64 * s + 16 * half);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 32, lo);
+          {
+            const float4* bh = reinterpret_cast<const float4*>(st + TILE_BYTES);
+            float4* bl = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + 2 * TILE_BYTES);
+#pragma unroll
+            for (int i = 0; i < TILE_BYTES / 16 / kConvThreads; ++i) {
+              const int q = ct + kConvThreads * i;
+              const float4 x = bh[q];
+              float4 l;
+              l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+              l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+              l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+              l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+              bl[q] = l;
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          proxy_fence_async();
+          mbar_arrive(full_ab(s));
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (!ATx::kActive && warp < 8) {
     // ================================================================ converter (128 threads, thread = A row)
     reg_dec<kConvRegs>();
     const int t = threadIdx.x - 128;
@@ -366,29 +462,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 x = row[c ^ (t & 7)];
             hi[4 * c + 0] = __float_as_uint(x.x); hi[4 * c + 1] = __float_as_uint(x.y);
             hi[4 * c + 2] = __float_as_uint(x.z); hi[4 * c + 3] = __float_as_uint(x.w);
-          }
-          if constexpr (ATx::kActive) {
-            // hi[] holds g_eo[row, c0 .. c0+31]; the second tile holds t: build g_t in place and store it
-            const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
-            const int c0 = (int)(kbeg + (int64_t)kb * BK);
-            const int64_t m = (int64_t)mt * BM + t;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 tv = row2[c ^ (t & 7)];
-              const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
-              float gt[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int ch = c0 + 4 * c + j;
-                const float4 ca = coef[2 * ch], cb = coef[2 * ch + 1];     // warp-uniform address: smem broadcast
-                const float xh = fmaf(tt[j], ca.x, ca.y);
-                const float gn = fmaf(xh, ca.z, ca.w) > 0.f ? __uint_as_float(hi[4 * c + j]) : 0.f;
-                gt[j] = fmaf(cb.x, gn, -cb.y) - xh * cb.z;
-                hi[4 * c + j] = __float_as_uint(gt[j]);
-              }
-              if (nt == 0 && m < g.M)
-                *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + c0 + 4 * c) = make_float4(gt[0], gt[1], gt[2], gt[3]);
-            }
           }
         } else {
           // MN-major 128B_ATOM_32B tile: box t/32 (4 KB), k-row k at k*128 B, m' = t%32 lives in 32-byte chunk
@@ -442,9 +515,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // walks the tile row-wise (4 threads x float4 = one 64-byte row segment) so that all global traffic of
     // the fused epilogue is coalesced.
     reg_inc<kEpiRegs>();
-    const int grp = (warp - 8) >> 2;
+    const int grp = (warp - kEpiWarp0) >> 2;
     const int ew = warp & 3;                            // TMEM lanes 32*ew .. 32*ew+31
-    const int tg = (threadIdx.x - 256) & 127;           // thread in group == accumulator row of the tile
+    const int tg = (threadIdx.x - kEpiThread0) & 127;   // thread in group == accumulator row of the tile
     const uint32_t bar_id = 1 + grp;
     float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
     int* idx_base = sidx + grp * 4 * BM;                // [2 buffers][src | dst][128]
@@ -691,7 +764,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
     attr_set = true;
   }
   GG_KERNEL_BEGIN(tag, st);
-  kern<<<grid, THREADS, kSmem, st>>>(tmA, tmB, tmA2, g, epi, atx);
+  kern<<<grid, threads<ATx>(), kSmem, st>>>(tmA, tmB, tmA2, g, epi, atx);
   GG_KERNEL_END(tag, st);
   return GG_OK;
 }

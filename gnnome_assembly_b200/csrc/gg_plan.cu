@@ -4,6 +4,8 @@
 // src/dst, which here is simply "walk the out-edge CSR instead of the in-edge CSR".
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -67,9 +69,7 @@ static void free_plan(Plan* p) {
   if (!p) return;
   free_sub_scratch(reinterpret_cast<SubScratch*>(p->sub_scratch));
   if (p->slab) { delete p; return; }      // sub-graph plan: the arrays live in a caller-owned slab
-  cudaFree(p->src); cudaFree(p->dst); cudaFree(p->in_ptr); cudaFree(p->out_ptr);
-  cudaFree(p->out_eid); cudaFree(p->out_dst); cudaFree(p->perm); cudaFree(p->inv_perm);
-  cudaFree(p->node_perm); cudaFree(p->node_inv);
+  cudaFree(p->host_slab);                 // gg_plan_create: one library-owned slab
   delete p;
 }
 
@@ -133,6 +133,14 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
   GG_REQUIRE(N >= 0 && E >= 0, "plan_create: negative size");
   GG_REQUIRE(N < (1LL << 31) && E < (1LL << 31), "plan_create: int32 indices only");
   GG_REQUIRE(E == 0 || (src && dst), "plan_create: null edge list");
+  const bool timing = std::getenv("GG_PLAN_TIMING") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "gg_plan_create: %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
   std::vector<int32_t> hs((size_t)E), hd((size_t)E);
   if (E > 0) {
     if (gg::is_device_ptr(src)) {
@@ -187,6 +195,7 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
   }
   for (int64_t p = 0; p < N; ++p) node_inv[node_perm[p]] = (int32_t)p;
   for (int64_t i = 0; i < E; ++i) { hs[i] = node_inv[hs[i]]; hd[i] = node_inv[hd[i]]; }
+  lap("copy+relabel");
 
   // stable counting sort by dst -> internal order
   std::vector<int32_t> in_ptr((size_t)N + 1, 0), out_ptr((size_t)N + 1, 0);
@@ -213,34 +222,36 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
     }
   }
 
+  lap("sort+csr");
   Plan* pl = new Plan();
   pl->N = N; pl->E = E;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
-  auto up = [&](int32_t** d, const std::vector<int32_t>& h) -> cudaError_t {
-    const size_t bytes = (h.size() ? h.size() : 1) * sizeof(int32_t);
-    cudaError_t e = cudaMalloc((void**)d, bytes);
-    if (e != cudaSuccess) return e;
-    if (h.size()) e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
-    return e;
+  // one device slab, one H2D copy: [src | dst | out_eid | out_dst | perm | inv_perm | in_ptr | out_ptr | node_perm | node_inv]
+  const size_t e1 = (size_t)(E ? E : 1), n1 = (size_t)N + 1;
+  const size_t words = 6 * e1 + 4 * n1;
+  std::vector<int32_t> stage(words, 0);
+  int32_t* slab = nullptr;
+  cudaError_t e = cudaMalloc((void**)&slab, words * sizeof(int32_t));
+  if (e != cudaSuccess) { delete pl; return gg::cuda_fail(e, "plan_create alloc"); }
+  pl->host_slab = slab;
+  size_t off = 0;
+  auto put = [&](int32_t** d, const std::vector<int32_t>& h, size_t cap) {
+    *d = slab + off;
+    if (!h.empty()) std::memcpy(stage.data() + off, h.data(), h.size() * sizeof(int32_t));
+    off += cap;
   };
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = up(&pl->src, isrc);
-  if (e == cudaSuccess) e = up(&pl->dst, idst);
-  if (e == cudaSuccess) e = up(&pl->in_ptr, in_ptr);
-  if (e == cudaSuccess) e = up(&pl->out_ptr, out_ptr);
-  if (e == cudaSuccess) e = up(&pl->out_eid, out_eid);
-  if (e == cudaSuccess) e = up(&pl->out_dst, out_dst);
-  if (e == cudaSuccess) e = up(&pl->perm, perm);
-  if (e == cudaSuccess) e = up(&pl->inv_perm, inv);
-  if (e == cudaSuccess) e = up(&pl->node_perm, node_perm);
-  if (e == cudaSuccess) e = up(&pl->node_inv, node_inv);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // host staging vectors die at return
+  put(&pl->src, isrc, e1); put(&pl->dst, idst, e1); put(&pl->out_eid, out_eid, e1); put(&pl->out_dst, out_dst, e1);
+  put(&pl->perm, perm, e1); put(&pl->inv_perm, inv, e1);
+  put(&pl->in_ptr, in_ptr, n1); put(&pl->out_ptr, out_ptr, n1); put(&pl->node_perm, node_perm, n1); put(&pl->node_inv, node_inv, n1);
+  e = cudaMemcpyAsync(slab, stage.data(), words * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // the host staging vector dies at return
   if (e != cudaSuccess) {
     gg::free_plan(pl);
     return gg::cuda_fail(e, "plan_create upload");
   }
+  lap("alloc+upload");
   *out = reinterpret_cast<gg_plan_t*>(pl);
   return GG_OK;
 }
