@@ -162,7 +162,7 @@ def algorithmic_bytes(E, N, d, H=64):
         "edge_bwd_a_kernel": 16 * d * E + 28 * d * N + 4 * E,           # read t,e_in,g_e; write g_eo; Gf,Gb,A2h,A3h; gA3h
         "edge_bwd_b_kernel": 12 * d * E + 4 * d * N,                    # read t,g_eo; write g_t; gB2h
         "edge_bwd_src_kernel": 8 * d * E + 12 * d * N + 8 * E,          # read g_t,e_out; gnf; write gB1h,gA2h
-        "gemm_bwd_e_in": 12 * d * E,                                    # read g_t,g_eo; write g_e_in
+        "gemm_bwd_e_in": 16 * d * E,                                    # BN path (A transform): read g_eo,t; write g_t,g_e_in
         "gemm_dB3": 8 * d * E,                                          # read g_t,e_in
         "gemm_bwd_h_in": 20 * d * N + 8 * d * N,
         "gemm_dWn": 20 * d * N + 4 * d * N,

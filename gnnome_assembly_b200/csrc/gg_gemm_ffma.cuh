@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_ffma_kernel(GemmArgs g, 
 struct EpiBias {
   float* C; int64_t ldc; const float* bias; int relu;
   static constexpr bool kIdx = false;
+  static constexpr bool kWideStaging = true;      // tensor-core kernel: 64-column staging tile, 3 stages
   struct PreD {};
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
@@ -286,6 +287,7 @@ struct EpiAddMaskT {
     else *reinterpret_cast<float2*>(C + m * ldc + n) = make_float2(acc[0], acc[1]);
   }
   static constexpr bool kIdx = false;
+  static constexpr bool kWideStaging = false;
   struct Empty {};
   struct Val { float4 v; };
   using PreD = typename std::conditional<kAdd, Val, Empty>::type;
@@ -311,6 +313,7 @@ struct EpiAddMaskT {
 struct EpiAtomic {
   float* C; int64_t ldc;
   static constexpr bool kIdx = false;
+  static constexpr bool kWideStaging = false;
   struct PreD {};
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
@@ -331,6 +334,7 @@ struct EpiAtomic {
 struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
+  static constexpr bool kWideStaging = true;      // fused gathers + statistics: the epilogue is the longer side
   struct PreD { float4 p1; };     // B1h[src]: random row gather -> a whole tile ahead
   struct PreN { float4 p2; };     // B2h[dst]: edges are dst-sorted, consecutive rows share it -> one chunk ahead
   __device__ __forceinline__ void prefetch_deep(PreD& p, int64_t, int n, int s, int) const {

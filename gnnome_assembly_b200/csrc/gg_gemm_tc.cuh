@@ -34,20 +34,34 @@ namespace gg {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;                         // (3 when the A operand is built from two streamed tiles)
+constexpr int STAGES = 4;                         // barrier-slot stride (3 stages are in use)
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A tile == B tile size since BM == BN)
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // A raw | B hi (raw) | B lo   (+ a second A tile with an A transform)
-constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;  // 192 KB either way (4 x 48 KB or 3 x 64 KB)
 constexpr int COEF_BYTES = 8 * 256 * 4;           // A-transform coefficients: 2 float4 per channel, K <= 256 channels
-constexpr int EC = 16;                            // epilogue chunk: 16 accumulator columns at a time
-constexpr int STAGING_BYTES = 2 * BM * EC * 4;    // one 8 KB staging tile per epilogue group (xor-swizzled float4s)
 constexpr int STATS_BYTES = 4 * BN * 2 * 8;       // [4 lane quarters][128 cols][sum, sumsq] doubles
 constexpr int IDX_BYTES = 2 * 2 * 2 * BM * 4;     // per epilogue group, double buffered: src / dst node ids of 128 rows
 constexpr int BAR_BYTES = 256;
+// Shared-memory budget (227 KB), three layouts:
+//   plain      : 4 stages of A raw | B hi (raw) | B lo = 4 x 48 KB, staging 2 x 8 KB (16-column chunks)
+//   wide       : 3 stages (144 KB), which leaves room for a staging tile of the epilogue group's WHOLE 64 columns
+//                (2 x 32 KB): one barrier pair per tile instead of one per 16-column chunk, 256-byte row segments
+//                in every global access, column statistics reduced once per tile
+//   A transform: 3 stages that also hold the second streamed A tile = 3 x 64 KB; staging 2 x 8 KB
+template <class ATx, class Epi>
+struct Cfg {
+  // wide staging pays where the epilogue is the longer side (fused gathers + statistics, plain stores of wide
+  // outputs): measured gemm_edge_gate 159 -> 154 us, gemm_node_proj 67 -> 63 us; the split-K weight gradients and
+  // the bwd-data GEMMs have long K loops and lose more from the fourth stage than they gain (79 -> 88 us)
+  static constexpr bool kWide = !ATx::kActive && Epi::kWideStaging;
+  static constexpr int kStages = (ATx::kActive || kWide) ? 3 : 4;
+  static constexpr int kStageBytes = (ATx::kActive ? 4 : 3) * TILE_BYTES;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kEC = kWide ? 64 : 16;                     // epilogue chunk width in accumulator columns
+  static constexpr int kStagingBytes = 2 * BM * kEC * 4;
+};
 template <bool kStats, class Epi, class ATx>
 constexpr int smem_bytes() {
-  return 1024 /*align slack*/ + PIPE_BYTES + STAGING_BYTES + (kStats ? STATS_BYTES : 0) + (Epi::kIdx ? IDX_BYTES : 0) +
-         BAR_BYTES + (ATx::kActive ? COEF_BYTES : 0);
+  return 1024 /*align slack*/ + Cfg<ATx, Epi>::kPipeBytes + Cfg<ATx, Epi>::kStagingBytes + (kStats ? STATS_BYTES : 0) +
+         (Epi::kIdx ? IDX_BYTES : 0) + BAR_BYTES + (ATx::kActive ? COEF_BYTES : 0);
 }
 constexpr int THREADS = 512;                      // 4 control + 4 converter + 8 epilogue warps
 constexpr int THREADS_ATX = 640;                  // an A transform doubles the converter: 4 + 8 + 8 warps
@@ -220,8 +234,8 @@ __global__ void __launch_bounds__(threads<ATx>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, Args g, Epi epi, ATx atx) {
   static_assert(!ATx::kActive || !A_MN, "A transforms are written for K-major A");
-  constexpr int kStages = ATx::kActive ? 3 : 4;
-  constexpr int kStageBytes = (ATx::kActive ? 4 : 3) * TILE_BYTES;
+  constexpr int kStages = Cfg<ATx, Epi>::kStages;
+  constexpr int kStageBytes = Cfg<ATx, Epi>::kStageBytes;
   // warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle | converters | 8 epilogue warps.
   // With an A transform the converter is the longest stage of the pipeline (ncu: its warps never wait), so it
   // gets 8 warps: warps w and w + 4 share a TMEM lane quarter and each takes 16 of the K-block's 32 columns.
@@ -233,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
-  constexpr int OFF_STG = PIPE_BYTES, OFF_STAT = OFF_STG + STAGING_BYTES, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
+  constexpr int OFF_STG = Cfg<ATx, Epi>::kPipeBytes, OFF_STAT = OFF_STG + Cfg<ATx, Epi>::kStagingBytes, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
                 OFF_BAR = OFF_IDX + (Epi::kIdx ? IDX_BYTES : 0), OFF_COEF = OFF_BAR + BAR_BYTES;
   float4* coef = reinterpret_cast<float4*>(gen + OFF_COEF);   // [K][2]: {p0, p1, gamma, beta}, {q0, q1, q2, -} (ATx only)
   float* staging = reinterpret_cast<float*>(gen + OFF_STG);
@@ -519,9 +533,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp & 3;                            // TMEM lanes 32*ew .. 32*ew+31
     const int tg = (threadIdx.x - kEpiThread0) & 127;   // thread in group == accumulator row of the tile
     const uint32_t bar_id = 1 + grp;
+    // chunk geometry: EC accumulator columns per chunk; a chunk row is TPR float4s, so TPR threads share a row and
+    // the group's 128 threads cover RPP rows per pass, PPC passes per chunk; QN chunks per 64-column group
+    constexpr int EC = Cfg<ATx, Epi>::kEC, TPR = EC / 4, RPP = 128 / TPR, PPC = 128 / RPP, QN = 64 / EC;
     float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
     int* idx_base = sidx + grp * 4 * BM;                // [2 buffers][src | dst][128]
-    const int c4 = (tg & 3) * 4;                        // column offset of this thread inside a chunk
+    const int tcol = tg % TPR, trow = tg / TPR;             // this thread's float4 column / row inside a pass
+    const int c4 = tcol * 4;                              // column offset of this thread inside a chunk
+    auto swz = [](int row) { return EC == 16 ? ((row >> 1) & 3) : (row & (TPR - 1)); };   // staging xor-swizzle
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     using PreD = typename Epi::PreD;
     using PreN = typename Epi::PreN;
@@ -530,24 +549,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // nothing is fetched while a tile is being consumed: a warp has only six load scoreboards, so a load
     // issued between two uses would make the older, already-landed operands wait for it.  The batch lands
     // while this group waits for the next accumulator (the MMA main loop of a tile is longer than a DRAM trip).
-    PreD deep[4][4];                                    // [chunk][pass]
-    PreN near[4][4];
+    PreD deep[QN][PPC];                                 // [chunk][pass]: 16 float4 slots either way
+    PreN near[QN][PPC];
 
     auto row_of = [&](int mt_, int p) {
-      int64_t m = (int64_t)mt_ * BM + p * 32 + (tg >> 2);
+      int64_t m = (int64_t)mt_ * BM + p * RPP + trow;
       return m < g.M ? m : g.M - 1;
     };
     auto col_of = [&](int nt_, int q) { return nt_ * BN + 64 * grp + EC * q + c4; };
     auto fetch_tile = [&](int mt_, int nt_, int buf) {
       if (g.dbg & 2) return;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int r = p * 32 + (tg >> 2);
+      for (int p = 0; p < PPC; ++p) {
+        const int r = p * RPP + trow;
         int sv = 0, dv = 0;
         if constexpr (Epi::kIdx) { sv = idx_base[buf * 2 * BM + r]; dv = idx_base[buf * 2 * BM + BM + r]; }
         const int64_t m = row_of(mt_, p);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < QN; ++q) {
           epi.prefetch_deep(deep[q][p], m, col_of(nt_, q), sv, dv);
           epi.prefetch_near(near[q][p], m, col_of(nt_, q), sv, dv);
         }
@@ -589,22 +608,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int64_t m0 = (int64_t)mt * BM;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[EC];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q), v);
-        if (q == 3) {                                   // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tmem_empty(acc));
-        }
+      for (int q = 0; q < QN; ++q) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg[tg * 4 + (j ^ ((tg >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int sub = 0; sub < EC / 16; ++sub) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v);
+          if (q == QN - 1 && sub == EC / 16 - 1) {      // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            stg[tg * TPR + ((4 * sub + j) ^ swz(tg))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
         group_bar();
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int r = p * 32 + (tg >> 2);
-          const float4 x = stg[r * 4 + ((tg & 3) ^ ((r >> 1) & 3))];
+        for (int p = 0; p < PPC; ++p) {
+          const int r = p * RPP + trow;
+          const float4 x = stg[r * TPR + (tcol ^ swz(r))];
           float a[4] = {x.x, x.y, x.z, x.w};
           const int64_t m = m0 + r;
           const int n = col_of(nt, q);
@@ -618,17 +640,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (kStats && !(g.dbg & 1)) {
-          // column statistics: fp32 over this chunk's 128 rows (4 per thread, then the 8 lanes l, l+4, ..,
-          // l+28 that own the same 4 columns), fp64 from there on
+          // column statistics: fp32 over this chunk's 128 rows (PPC per thread, then the 32 / TPR lanes that own
+          // the same 4 columns), fp64 from there on
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
+            for (int o = TPR; o < 32; o <<= 1) {
               s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
               s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
             }
           }
-          if (lane < 4) {
+          if (lane < TPR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 0] += (double)s1[j];
