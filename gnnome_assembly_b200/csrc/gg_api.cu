@@ -380,6 +380,11 @@ int gg_score_fwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
   int rc = linear_fwd("gemm_score_q", pl->N, 2 * H, d, x, d, Wq, d, bq, 0, Q, 2 * H, st);
   if (rc) return rc;
   if (pl->E == 0) return GG_OK;
+  if (g_tc_mode && d % tc::BK == 0 && reinterpret_cast<uintptr_t>(e) % 16 == 0 && reinterpret_cast<uintptr_t>(W1e) % 16 == 0) {
+    EpiScoreTC epi{score, hid, Q, w2, b2, pl->src, pl->dst};
+    return tc::launch<false, false, false, false>("gemm_score", e, d, W1e, d, pl->E, H, d, 1, nullptr, nullptr, epi,
+                                                  sm_count(), st);
+  }
   GemmArgs g{};
   g.A = e; g.lda = d; g.B = W1e; g.ldb = d; g.M = pl->E; g.N = H; g.K = d;
   EpiScore epi{score, hid, Q, w2, b2, pl->src, pl->dst, pl->E};

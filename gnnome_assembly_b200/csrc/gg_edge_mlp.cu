@@ -1,0 +1,148 @@
+// gg_edge_mlp.cu — backward of the edge encoder  e0 = W2 relu(W1 e + b1) + b2  (models/full_graph.py:17-18,24-26)
+// in ONE pass over the E x d gradient.
+//
+// As three GEMM calls (dW2 = g^T hid, g_hid = (g W2) [hid > 0], dW1 = g_hid^T e) the E x d gradient is read
+// twice by narrow-N FFMA kernels (N = 16) that run far from both rooflines (150 + 200 us on the chr19 graph,
+// HBM time of one read: 30 us).  Here one warp owns a row at a time: lane l holds the row's channels
+// Row<D>::channel(., l), the lane's rows of W2 live in registers for the whole kernel, dW2 / db2 accumulate in
+// registers, the 16 hidden-unit sums are reduced across the warp with a transpose-reduce (16 shuffles instead
+// of 80) and land one per lane pair, so g_hid is never written: dW1 / db1 are accumulated in place.
+#include "gg_common.cuh"
+
+namespace gg {
+
+constexpr int kMlpThreads = 256;
+constexpr int kMlpHid = 16, kMlpK = 4;       // hidden_edge_features = 16 (hyperparameters.py:11), edge_features 2 padded to 4
+
+template <int D>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restrict__ hid, const float* __restrict__ e,
+                    const float* __restrict__ W2, float* __restrict__ dW1, float* __restrict__ db1,
+                    float* __restrict__ dW2, float* __restrict__ db2) {
+  constexpr int VPL = D / 32, H = kMlpHid;
+  constexpr int kOut = D * H + D + H * kMlpK + H;            // dW2 | db2 | dW1 | db1
+  __shared__ float red[kOut];
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * kMlpThreads + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * kMlpThreads) >> 5;
+  for (int i = threadIdx.x; i < kOut; i += kMlpThreads) red[i] = 0.f;
+
+  float w[VPL][H], a2[VPL][H], ab2[VPL], a1[kMlpK], ab1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = Row<D>::channel(i, lane);
+    ab2[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(W2 + (int64_t)c * H + k));
+      w[i][k] = x.x; w[i][k + 1] = x.y; w[i][k + 2] = x.z; w[i][k + 3] = x.w;
+      a2[i][k] = 0.f; a2[i][k + 1] = 0.f; a2[i][k + 2] = 0.f; a2[i][k + 3] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMlpK; ++j) a1[j] = 0.f;
+  const int my_k = lane >> 1;                                // the hidden unit this lane pair ends up owning
+
+  // software pipeline: the next row's operands are requested before the current row is processed (8 warps per
+  // SM cannot hide a DRAM round trip per row on their own)
+  Row<D> gn;
+  float4 hn[H / 4], en;
+  float hkn;
+  auto fetch = [&](int64_t row) {
+    gn.load_stream(g + row * D, lane);
+#pragma unroll
+    for (int k = 0; k < H / 4; ++k) hn[k] = __ldg(reinterpret_cast<const float4*>(hid + row * H) + k);   // same address in every lane
+    en = __ldg(reinterpret_cast<const float4*>(e + row * kMlpK));
+    hkn = __ldg(hid + row * H + my_k);
+  };
+  if (gw < E) fetch(gw);
+  for (int64_t row = gw; row < E; row += nw) {
+    const Row<D> gr = gn;
+    float h[H];
+#pragma unroll
+    for (int k = 0; k < H / 4; ++k) { h[4 * k] = hn[k].x; h[4 * k + 1] = hn[k].y; h[4 * k + 2] = hn[k].z; h[4 * k + 3] = hn[k].w; }
+    const float4 ev = en;
+    const float hk = hkn;
+    if (row + nw < E) fetch(row + nw);
+    float v[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      ab2[i] += gr.v[i];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        v[k] = fmaf(gr.v[i], w[i][k], v[k]);                 // partial (g W2)[k] over this lane's channels
+        a2[i][k] = fmaf(gr.v[i], h[k], a2[i][k]);            // dW2[c][k] += g[c] hid[k]
+      }
+    }
+    // transpose-reduce: after the step with offset o, a lane keeps the half of its values selected by (lane & o)
+#pragma unroll
+    for (int o = 16, n = H / 2; o >= 2; o >>= 1, n >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const float send = up ? v[j] : v[j + n];
+        const float keep = up ? v[j + n] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);           // both lanes of the pair: (g W2)[lane >> 1]
+    const float gh = hk > 0.f ? v[0] : 0.f;                  // ReLU backward
+    a1[0] = fmaf(gh, ev.x, a1[0]); a1[1] = fmaf(gh, ev.y, a1[1]);
+    a1[2] = fmaf(gh, ev.z, a1[2]); a1[3] = fmaf(gh, ev.w, a1[3]);
+    ab1 += gh;
+  }
+
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = Row<D>::channel(i, lane);
+#pragma unroll
+    for (int k = 0; k < H; ++k) atomicAdd(&red[c * H + k], a2[i][k]);
+    atomicAdd(&red[D * H + c], ab2[i]);
+  }
+  if ((lane & 1) == 0) {
+#pragma unroll
+    for (int j = 0; j < kMlpK; ++j) atomicAdd(&red[D * H + D + my_k * kMlpK + j], a1[j]);
+    atomicAdd(&red[D * H + D + H * kMlpK + my_k], ab1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kOut; i += kMlpThreads) {
+    const float x = red[i];
+    float* dst = i < D * H ? dW2 + i : i < D * H + D ? db2 + (i - D * H)
+               : i < D * H + D + H * kMlpK ? dW1 + (i - D * H - D) : db1 + (i - D * H - D - H * kMlpK);
+    atomicAdd(dst, x);
+  }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_edge_mlp_bwd(int64_t E, int d, int hidden, int K, const float* g, const float* hid, const float* e,
+                               const float* W2, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+  GG_REQUIRE(E >= 0, "edge_mlp_bwd: negative size");
+  if (hidden != kMlpHid || K != kMlpK || !(d == 64 || d == 128)) {
+    set_error("gnnome_b200: edge_mlp_bwd is built for hidden_edge_features = 16, K = 4 (2 padded), d in {64,128}");
+    return GG_ERR_UNSUPPORTED;
+  }
+  GG_REQUIRE(W2 && dW1 && db1 && dW2 && db2, "edge_mlp_bwd: null parameter / output");
+  GG_REQUIRE(E == 0 || (g && hid && e), "edge_mlp_bwd: null edge buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)d * hidden, st));
+  GG_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * (size_t)d, st));
+  GG_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)hidden * K, st));
+  GG_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * (size_t)hidden, st));
+  if (E == 0) return GG_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  int64_t blocks = (E + 7) / 8;
+  if (blocks > sms) blocks = sms;                             // one persistent CTA per SM (register-heavy)
+  GG_KERNEL_BEGIN("edge_mlp_bwd_kernel", st);
+  if (d == 64) edge_mlp_bwd_kernel<64><<<(unsigned)blocks, kMlpThreads, 0, st>>>(E, g, hid, e, W2, dW1, db1, dW2, db2);
+  else edge_mlp_bwd_kernel<128><<<(unsigned)blocks, kMlpThreads, 0, st>>>(E, g, hid, e, W2, dW1, db1, dW2, db2);
+  GG_KERNEL_END("edge_mlp_bwd_kernel", st);
+  return GG_OK;
+}

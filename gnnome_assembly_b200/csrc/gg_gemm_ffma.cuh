@@ -247,6 +247,7 @@ struct EpiBias {
   float* C; int64_t ldc; const float* bias; int relu;
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = true;      // tensor-core kernel: 64-column staging tile, 3 stages
+  static constexpr bool kRowReduce = false;
   struct PreD {};
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
@@ -288,6 +289,7 @@ struct EpiAddMaskT {
   }
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = false;
+  static constexpr bool kRowReduce = false;
   struct Empty {};
   struct Val { float4 v; };
   using PreD = typename std::conditional<kAdd, Val, Empty>::type;
@@ -314,6 +316,7 @@ struct EpiAtomic {
   float* C; int64_t ldc;
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = false;
+  static constexpr bool kRowReduce = false;
   struct PreD {};
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
@@ -335,6 +338,7 @@ struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
   static constexpr bool kWideStaging = true;      // fused gathers + statistics: the epilogue is the longer side
+  static constexpr bool kRowReduce = false;
   struct PreD { float4 p1; };     // B1h[src]: random row gather -> a whole tile ahead
   struct PreN { float4 p2; };     // B2h[dst]: edges are dst-sorted, consecutive rows share it -> one chunk ahead
   __device__ __forceinline__ void prefetch_deep(PreD& p, int64_t, int n, int s, int) const {
@@ -395,6 +399,40 @@ struct EpiScore {
       if ((threadIdx.x & 15) == 0) score[m] = part + __ldg(b2);
     }
   }
+};
+
+// the same on the tensor-core kernel (wide staging: the 16 threads that share a row sit in one half-warp).
+// N = 64 < BN: the TMA box of the B operand reaches past W1e's 64 rows and is zero-filled, the upper 64
+// accumulator columns are never valid.
+struct EpiScoreTC {
+  float* score; float* hid; const float* Q; const float* w2; const float* b2; const int32_t* src; const int32_t* dst;
+  static constexpr bool kIdx = true;
+  static constexpr bool kWideStaging = true;
+  static constexpr bool kRowReduce = true;
+  static constexpr int H = 64;
+  struct PreD { float4 q1; };     // Q[src, n]
+  struct PreN { float4 q2; };     // Q[dst, H + n]
+  __device__ __forceinline__ void prefetch_deep(PreD& p, int64_t, int n, int s, int) const {
+    if (n < H) p.q1 = __ldg(reinterpret_cast<const float4*>(Q + (int64_t)s * (2 * H) + n));
+  }
+  __device__ __forceinline__ void prefetch_near(PreN& p, int64_t, int n, int, int v) const {
+    if (n < H) p.q2 = __ldg(reinterpret_cast<const float4*>(Q + (int64_t)v * (2 * H) + H + n));
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, bool valid) const {
+    if (!valid) { acc[0] = acc[1] = acc[2] = acc[3] = 0.f; return; }
+    acc[0] = fmaxf(acc[0] + d.q1.x + p.q2.x, 0.f);
+    acc[1] = fmaxf(acc[1] + d.q1.y + p.q2.y, 0.f);
+    acc[2] = fmaxf(acc[2] + d.q1.z + p.q2.z, 0.f);
+    acc[3] = fmaxf(acc[3] + d.q1.w + p.q2.w, 0.f);
+    if (hid) *reinterpret_cast<float4*>(hid + m * H + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+  // this thread's share of the row's dot product with w2 (0 for invalid elements: acc was zeroed)
+  __device__ __forceinline__ float row_partial(const float (&acc)[4], int n) const {
+    if (n >= H) return 0.f;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + n));
+    return acc[0] * w.x + acc[1] * w.y + acc[2] * w.z + acc[3] * w.w;
+  }
+  __device__ __forceinline__ void row_finish(int64_t m, float sum) const { score[m] = sum + __ldg(b2); }
 };
 
 // ------------------------------------------------------------------------------------ launcher

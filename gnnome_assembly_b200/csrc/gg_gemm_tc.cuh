@@ -632,6 +632,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int n = col_of(nt, q);
           const bool valid = (m < g.M) && (n < g.N);
           epi.apply_pre(m, n, a, deep[q][p], near[q][p], valid);
+          if constexpr (Epi::kRowReduce) {
+            // one scalar per output row: the TPR threads of the row are consecutive lanes (wide staging only)
+            static_assert(!Epi::kRowReduce || EC == 64, "row reductions need the 64-column staging tile");
+            float part = epi.row_partial(a, n);
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (tcol == 0 && grp == 0 && m < g.M) epi.row_finish(m, part);
+          }
           if constexpr (kStats) {
             if (valid && !(g.dbg & 1)) {
 #pragma unroll
@@ -767,7 +775,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   Args g{};
   g.M = M; g.N = N; g.K = K;
   g.m_tiles = (int)((M + BM - 1) / BM);
-  g.n_tiles = N / BN;
+  g.n_tiles = (N + BN - 1) / BN;                 // N < BN: the B box is zero-filled past N, columns >= N are never valid
   if (splits < 1) splits = 1;
   int64_t chunk = (K + splits - 1) / splits;
   chunk = ((chunk + BK - 1) / BK) * BK;

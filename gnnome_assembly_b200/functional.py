@@ -131,6 +131,13 @@ class _EdgeMLP(torch.autograd.Function):
         Hh, d = W1.shape[0], W2.shape[0]
         dW2 = torch.empty_like(W2)
         db2 = torch.empty(d, device=g.device, dtype=torch.float32)
+        if Hh == 16 and K == 4 and d in (64, 128):
+            # one pass over g: dW2, db2, the ReLU-masked hidden gradient (never stored), dW1, db1
+            dW1 = torch.empty_like(W1)
+            db1 = torch.empty(Hh, device=g.device, dtype=torch.float32)
+            check(lib.gg_edge_mlp_bwd(E, d, Hh, K, ptr(g), ptr(hid), ptr(e), ptr(W2), ptr(dW1), ptr(db1), ptr(dW2),
+                                      ptr(db2), _stream()), "gg_edge_mlp_bwd")
+            return None, dW1, db1, dW2, db2
         check(lib.gg_linear_bwd_weight(E, d, Hh, ptr(g), ptr(hid), ptr(dW2), ptr(db2), _stream()), "gg_linear_bwd_weight")
         g_hid = torch.empty_like(hid)
         check(lib.gg_linear_bwd_data(E, d, Hh, ptr(g), ptr(W2), None, ptr(hid), ptr(g_hid), _stream()), "gg_linear_bwd_data")

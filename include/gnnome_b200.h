@@ -184,6 +184,15 @@ int gg_bce_bwd(int64_t E, const float* scores, const float* y, float pos_weight,
  * caller's edge-id order (the contract at the model boundary) and the internal order. */
 int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx, float* out, void* stream);
 
+/* ---- edge encoder backward ------------------------------------------------------------------
+ * Autograd of linear2_edge(relu(linear1_edge(e))) (models/full_graph.py:24-26) in one pass over the E x d
+ * gradient g: dW2[d,hidden] = g^T hid, db2[d] = colsum g, g_hid = (g W2) * [hid > 0] (never stored),
+ * dW1[hidden,K] = g_hid^T e, db1[hidden] = colsum g_hid.  hid[E,hidden] = relu(W1 e + b1) from the forward,
+ * e[E,K] the (zero-padded) raw edge features.  Built for hidden = 16, K = 4, d in {64,128}; other shapes return
+ * GG_ERR_UNSUPPORTED and the caller uses gg_linear_bwd_weight / gg_linear_bwd_data.  Outputs are zeroed here. */
+int gg_edge_mlp_bwd(int64_t E, int d, int hidden, int K, const float* g, const float* hid, const float* e,
+                    const float* W2, float* dW1, float* db1, float* dW2, float* db2, void* stream);
+
 /* ---- greedy contig decoding -------------------------------------------------------------------
  * Replaces the body of get_contigs (inference.py:182-259): per decoding iteration the reference samples
  * nb_paths start edges and runs walk_forwards / walk_backwards (inference.py:31-77) for each of them one after
