@@ -1,0 +1,78 @@
+"""BASELINE.json configs[2]: the inference path of inference.py:324-369 on a chr21-like synthetic graph with the
+shipped checkpoint (model_15xchr19.pt: L=16, d=256, BatchNorm) — input preparation, edge-probability forward,
+metrics, greedy decode — every phase on the GPU, timed.  One JSON line.
+
+  python tools/infer_chr21.py            (falls back to random weights when the checkpoint is not in the tree)
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import gnnome_assembly_b200 as gg
+from gnnome_assembly_b200 import decode, prep
+from gnnome_assembly_b200.synth import make_assembly_graph
+
+dev = torch.device("cuda:0")
+gs = make_assembly_graph("chr21", seed=0)
+N, E = gs.num_nodes, gs.num_edges
+ckpt = os.path.join(ROOT, "tests", "golden", "_ref", "model_15xchr19.pt")
+torch.manual_seed(0)
+model = gg.GraphGatedGCNModel(1, 2, 256, 16, 16, 64, True, 16)
+weights = "random"
+if os.path.exists(ckpt):
+    model.load_state_dict(torch.load(ckpt, map_location="cpu"), strict=True)
+    weights = "model_15xchr19.pt"
+model.eval().to(dev)
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    return out, (time.perf_counter() - t0) * 1e3
+
+
+g = gg.AssemblyGraph(torch.from_numpy(gs.src.astype(np.int64)), torch.from_numpy(gs.dst.astype(np.int64)), N)
+_, t_h2d = timed(lambda: g.to(dev))
+g = g.to(dev)
+ol = torch.from_numpy(np.trunc(gs.overlap_length)).to(dev)
+sim = torch.from_numpy(gs.overlap_similarity).to(dev)
+y = torch.from_numpy(gs.y).to(dev)
+plan, t_plan = timed(lambda: gg.plan_for(g, dev))
+e, t_feat = timed(lambda: prep.preprocess_features(ol, sim))                       # utils.py:67-75
+pe, t_pe = timed(lambda: prep.positional_encoding(g, 16))                          # utils.py:97-138 + train.py:249-251
+with torch.no_grad():
+    model(g, None, e, pe)                                                          # warm-up (lazy init, allocator)
+    scores, t_fwd = timed(lambda: model(g, None, e, pe))                           # inference.py:335
+    (loss, tfpn), t_met = timed(lambda: prep.bce_with_logits_and_metrics(scores, y, 1.0))
+tp, tn, fp, fn = (float(x) for x in tfpn.tolist())
+g.edata["score"] = scores.squeeze(-1)
+g.edata["prefix_length"] = torch.from_numpy(gs.prefix_length).to(dev)
+g.ndata["read_length"] = torch.from_numpy(gs.read_length).to(dev)
+gen = torch.Generator(device="cuda").manual_seed(0)
+contigs, t_dec = timed(lambda: decode.get_contigs(g, None, None, None, 50, 20, device="cuda", generator=gen))
+# reference check of the forward on the CPU oracle when asked for (slow: L=16, d=256)
+err = None
+if "--check" in sys.argv:
+    from oracle.gatedgcn_oracle import OracleModel, rel_err
+    om = OracleModel(1, 2, 256, 16, 16, 64, True, 16)
+    om.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        ref = om(torch.from_numpy(gs.src.astype(np.int64)), torch.from_numpy(gs.dst.astype(np.int64)), N, e.cpu(), pe.cpu())
+    err = rel_err(scores.cpu(), ref)
+print(json.dumps({
+    "workload": f"configs[2]: chr21-like synthetic graph N={N} E={E}, {weights} (L=16 d=256), inference.py:324-369",
+    "ms": {"plan_host": t_plan, "zscore_features": t_feat, "positional_encoding": t_pe, "forward": t_fwd,
+           "loss_and_metrics": t_met, "decode_get_contigs": t_dec},
+    "forward_edges_per_s": E / t_fwd * 1e3,
+    "metrics": {"TP": tp, "TN": tn, "FP": fp, "FN": fn, "acc": (tp + tn) / max(tp + tn + fp + fn, 1)},
+    "contigs": {"count": len(contigs), "nodes": sum(len(c) for c in contigs), "longest": max((len(c) for c in contigs), default=0)},
+    "logit_rel_err_vs_cpu_oracle": err,
+}))
