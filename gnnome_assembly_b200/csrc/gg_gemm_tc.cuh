@@ -46,21 +46,28 @@ constexpr int BAR_BYTES = 256;
 //                (2 x 32 KB): one barrier pair per tile instead of one per 16-column chunk, 256-byte row segments
 //                in every global access, column statistics reduced once per tile
 //   A transform: 3 stages that also hold the second streamed A tile = 3 x 64 KB; staging 2 x 8 KB
-template <class ATx, class Epi>
+template <class ATx, class Epi, bool kWRes = false>
 struct Cfg {
   // wide staging pays where the epilogue is the longer side (fused gathers + statistics, plain stores of wide
   // outputs): measured gemm_edge_gate 159 -> 154 us, gemm_node_proj 67 -> 63 us; the split-K weight gradients and
   // the bwd-data GEMMs have long K loops and lose more from the fourth stage than they gain (79 -> 88 us)
-  static constexpr bool kWide = !ATx::kActive && Epi::kWideStaging;
-  static constexpr int kStages = (ATx::kActive || kWide) ? 3 : 4;
-  static constexpr int kStageBytes = (ATx::kActive ? 4 : 3) * TILE_BYTES;
-  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr bool kWide = !ATx::kActive && Epi::kWideStaging && !kWRes;
+  // W-resident (kWRes): the whole B operand (a d x d weight, K <= 128: 4 K-blocks of B_hi and of B_lo = 128 KB)
+  // is loaded and split ONCE per CTA; the ring then carries only A tiles.  The kernel is bound by the LSU /
+  // shared-memory pipe (ncu: l1tex 66-70 % busy, everything else < 40 %), and per K-block the B side was 16 KB of
+  // TMA writes + 32 KB of split traffic out of ~128 KB.
+  static constexpr int kStages = kWRes ? (ATx::kActive ? 2 : 4) : ((ATx::kActive || kWide) ? 3 : 4);
+  static constexpr int kATiles = ATx::kActive ? 2 : 1;
+  static constexpr int kStageBytes = (kWRes ? kATiles : kATiles + 2) * TILE_BYTES;
+  static constexpr int kOffA2 = kWRes ? TILE_BYTES : 3 * TILE_BYTES;        // second streamed A tile (A transform)
+  static constexpr int kBResBytes = kWRes ? 8 * TILE_BYTES : 0;            // [4 K-blocks hi][4 K-blocks lo]
+  static constexpr int kPipeBytes = kStages * kStageBytes + kBResBytes;
   static constexpr int kEC = kWide ? 64 : 16;                     // epilogue chunk width in accumulator columns
   static constexpr int kStagingBytes = 2 * BM * kEC * 4;
 };
-template <bool kStats, class Epi, class ATx>
+template <bool kStats, class Epi, class ATx, bool kWRes = false>
 constexpr int smem_bytes() {
-  return 1024 /*align slack*/ + Cfg<ATx, Epi>::kPipeBytes + Cfg<ATx, Epi>::kStagingBytes + (kStats ? STATS_BYTES : 0) +
+  return 1024 /*align slack*/ + Cfg<ATx, Epi, kWRes>::kPipeBytes + Cfg<ATx, Epi, kWRes>::kStagingBytes + (kStats ? STATS_BYTES : 0) +
          (Epi::kIdx ? IDX_BYTES : 0) + BAR_BYTES + (ATx::kActive ? COEF_BYTES : 0);
 }
 constexpr int THREADS = 512;                      // 4 control + 4 converter + 8 epilogue warps
@@ -229,13 +236,15 @@ struct BnBwdATx {
 };
 
 // ---------------------------------------------------------------------------------- the kernel
-template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx>
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx, bool kWRes = false>
 __global__ void __launch_bounds__(threads<ATx>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, Args g, Epi epi, ATx atx) {
   static_assert(!ATx::kActive || !A_MN, "A transforms are written for K-major A");
-  constexpr int kStages = Cfg<ATx, Epi>::kStages;
-  constexpr int kStageBytes = Cfg<ATx, Epi>::kStageBytes;
+  constexpr int kStages = Cfg<ATx, Epi, kWRes>::kStages;
+  constexpr int kStageBytes = Cfg<ATx, Epi, kWRes>::kStageBytes;
+  constexpr int kOffA2 = Cfg<ATx, Epi, kWRes>::kOffA2;
+  static_assert(!kWRes || !A_MN, "W-resident mode is for K-major A (forward / bwd-data)");
   // warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle | converters | 8 epilogue warps.
   // With an A transform the converter is the longest stage of the pipeline (ncu: its warps never wait), so it
   // gets 8 warps: warps w and w + 4 share a TMEM lane quarter and each takes 16 of the K-block's 32 columns.
@@ -247,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // swizzle atoms need 1 KB alignment
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
-  constexpr int OFF_STG = Cfg<ATx, Epi>::kPipeBytes, OFF_STAT = OFF_STG + Cfg<ATx, Epi>::kStagingBytes, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
+  constexpr int OFF_STG = Cfg<ATx, Epi, kWRes>::kPipeBytes, OFF_STAT = OFF_STG + Cfg<ATx, Epi, kWRes>::kStagingBytes, OFF_IDX = OFF_STAT + (kStats ? STATS_BYTES : 0),
                 OFF_BAR = OFF_IDX + (Epi::kIdx ? IDX_BYTES : 0), OFF_COEF = OFF_BAR + BAR_BYTES;
   float4* coef = reinterpret_cast<float4*>(gen + OFF_COEF);   // [K][2]: {p0, p1, gamma, beta}, {q0, q1, q2, -} (ATx only)
   float* staging = reinterpret_cast<float*>(gen + OFF_STG);
@@ -260,6 +269,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tmem_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
   auto tmem_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+  const uint32_t bres_full = bars + 8u * 17, bres_ready = bars + 8u * 18;     // W-resident B: loaded / split
+  const uint32_t bres0 = stage0 + kStages * kStageBytes;                         // B_hi K-blocks, then B_lo K-blocks
+  const int nkb_total = (int)((g.K + BK - 1) / BK);                              // kWRes: <= 4
 
   // register split (setmaxnreg): a fused epilogue that holds a whole tile of prefetched operands gets more
   constexpr bool kHeavyEpi = (sizeof(typename Epi::PreD) + sizeof(typename Epi::PreN)) >= 32;
@@ -275,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), kConvThreads); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
+    if constexpr (kWRes) { mbar_init(bres_full, 1); mbar_init(bres_ready, kConvThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -318,19 +331,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     nkb = (int)((kend - kbeg + BK - 1) / BK);
   };
 
+  // W-resident B: split the whole operand once (element-wise at identical swizzled offsets, like the per-stage split)
+  auto split_resident_b = [&](int ct) {
+    if (blockIdx.x >= total_work) return;
+    mbar_wait(bres_full, 0u);
+    const float4* bh = reinterpret_cast<const float4*>(gen + kStages * kStageBytes);
+    float4* bl = reinterpret_cast<float4*>(gen + kStages * kStageBytes + 4 * TILE_BYTES);
+    const int total = nkb_total * (TILE_BYTES / 16);
+    for (int q = ct; q < total; q += kConvThreads) {
+      const float4 x = bh[q];
+      float4 l;
+      l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+      l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+      l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+      bl[q] = l;
+    }
+    proxy_fence_async();                               // generic-proxy smem writes -> visible to the tensor core
+    mbar_arrive(bres_ready);
+  };
+
   if (warp < 4) {
     reg_dec<kCtrlRegs>();
     if (warp == 0 && lane == 0) {
       // ================================================================ TMA producer
       int s = 0; uint32_t ph = 0;
+      if constexpr (kWRes) {
+        if (blockIdx.x < total_work) {
+          mbar_expect_tx(bres_full, (uint32_t)nkb_total * TILE_BYTES);
+          for (int kb = 0; kb < nkb_total; ++kb) {
+            if constexpr (!B_MN) {
+              tma_load_2d(bres0 + kb * TILE_BYTES, &tmB, bres_full, kb * BK, 0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_2d(bres0 + kb * TILE_BYTES + j * 4096, &tmB, bres_full, 32 * j, kb * BK);
+            }
+          }
+        }
+      }
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty(s), ph ^ 1u);
           const uint32_t st = stage0 + s * kStageBytes;
-          mbar_expect_tx(full_raw(s), (ATx::kActive ? 3 : 2) * TILE_BYTES);
-          if constexpr (ATx::kActive) tma_load_2d(st + 3 * TILE_BYTES, &tmA2, full_raw(s), (int)(kbeg + (int64_t)kb * BK), mt * BM);
+          mbar_expect_tx(full_raw(s), (Cfg<ATx, Epi, kWRes>::kATiles + (kWRes ? 0 : 1)) * TILE_BYTES);
+          if constexpr (ATx::kActive) tma_load_2d(st + kOffA2, &tmA2, full_raw(s), (int)(kbeg + (int64_t)kb * BK), mt * BM);
           const int k0 = (int)(kbeg + (int64_t)kb * BK);
           if constexpr (!A_MN) {
             tma_load_2d(st, &tmA, full_raw(s), k0, mt * BM);
@@ -338,11 +384,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) tma_load_2d(st + j * 4096, &tmA, full_raw(s), mt * BM + 32 * j, k0);
           }
-          if constexpr (!B_MN) {
-            tma_load_2d(st + TILE_BYTES, &tmB, full_raw(s), k0, nt * BN);
-          } else {
+          if constexpr (!kWRes) {
+            if constexpr (!B_MN) {
+              tma_load_2d(st + TILE_BYTES, &tmB, full_raw(s), k0, nt * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
+              for (int j = 0; j < 4; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, full_raw(s), nt * BN + 32 * j, k0);
+            }
           }
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
@@ -351,6 +399,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ================================================================ MMA issuer (one thread)
       constexpr uint32_t idesc = make_idesc(false, B_MN);          // A comes from TMEM: always K-major there
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+      if constexpr (kWRes) {
+        if (blockIdx.x < total_work) { mbar_wait(bres_ready, 0u); tc_fence_after(); }
+      }
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
@@ -362,8 +413,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t st = stage0 + s * kStageBytes;
           const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A0 + 64 * s), a_lo = a_hi + 32;
-          const uint64_t b_hi = make_desc<B_MN>(st + TILE_BYTES);
-          const uint64_t b_lo = make_desc<B_MN>(st + 2 * TILE_BYTES);
+          const uint64_t b_hi = make_desc<B_MN>(kWRes ? bres0 + kb * TILE_BYTES : st + TILE_BYTES);
+          const uint64_t b_lo = make_desc<B_MN>(kWRes ? bres0 + (4 + kb) * TILE_BYTES : st + 2 * TILE_BYTES);
           constexpr uint64_t b_step = B_MN ? (1024 >> 4) : (32 >> 4);   // 8 tf32 along K: 8 k-rows / 32 bytes
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
@@ -390,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int half = cw >> 2;
       const uint32_t lane_base = (uint32_t)(32 * (cw & 3)) << 16;
       int s = 0; uint32_t ph = 0;
+      if constexpr (kWRes) split_resident_b(ct);
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
@@ -399,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint8_t* st = gen + s * kStageBytes;
           // g_eo[row, c0 + 16 half ..+15] (tile 0) and t (tile 3) -> g_t (stored, and the A operand)
           const float4* row = reinterpret_cast<const float4*>(st + t * 128);
-          const float4* row2 = reinterpret_cast<const float4*>(st + 3 * TILE_BYTES + t * 128);
+          const float4* row2 = reinterpret_cast<const float4*>(st + kOffA2 + t * 128);
           const int c0 = (int)(kbeg + (int64_t)kb * BK);
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -430,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ta = tmem_base + lane_base + (uint32_t)(TMEM_A0 + 64 * s + 16 * half);
           tmem_st16(ta, hi);
           tmem_st16(ta + 32, lo);
-          {
+          if constexpr (!kWRes) {
             const float4* bh = reinterpret_cast<const float4*>(st + TILE_BYTES);
             float4* bl = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + 2 * TILE_BYTES);
 #pragma unroll
@@ -459,6 +511,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     int s = 0; uint32_t ph = 0;
+    if constexpr (kWRes) split_resident_b(t);
     for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, sp; decode(w, mt, nt, sp);
       int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
@@ -496,7 +549,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
         // ---- B_lo = B - trunc(B), element-wise at identical (swizzled) byte offsets
-        {
+        if constexpr (!kWRes) {
           const float4* bh = reinterpret_cast<const float4*>(st + TILE_BYTES);
           float4* bl = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + 2 * TILE_BYTES);
 #pragma unroll
@@ -535,7 +588,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar_id = 1 + grp;
     // chunk geometry: EC accumulator columns per chunk; a chunk row is TPR float4s, so TPR threads share a row and
     // the group's 128 threads cover RPP rows per pass, PPC passes per chunk; QN chunks per 64-column group
-    constexpr int EC = Cfg<ATx, Epi>::kEC, TPR = EC / 4, RPP = 128 / TPR, PPC = 128 / RPP, QN = 64 / EC;
+    constexpr int EC = Cfg<ATx, Epi, kWRes>::kEC, TPR = EC / 4, RPP = 128 / TPR, PPC = 128 / RPP, QN = 64 / EC;
     float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
     int* idx_base = sidx + grp * 4 * BM;                // [2 buffers][src | dst][128]
     const int tcol = tg % TPR, trow = tg / TPR;             // this thread's float4 column / row inside a pass
@@ -755,7 +808,7 @@ inline bool eligible(bool a_mn, bool b_mn, int64_t M, int N, int64_t K, int64_t 
 
 // C[M,N] = sum_k A(m,k) B(k,n).  A_MN: A stored [K, M] (lda) else [M, K];  B_MN: B stored [K, N] (ldb) else [N, K].
 // With an A transform, A2 is a second [M, K] operand streamed next to A (same lda).
-template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx = NoATx>
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx = NoATx, bool kWRes = false>
 int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
            int splits, double* col_stats, float* bias_grad, const Epi& epi, int num_sms, cudaStream_t st,
            const ATx& atx = ATx{}, const float* A2 = nullptr) {
@@ -786,8 +839,13 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   g.dbg = tc_dbg_ref();
   const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
   const int grid = (int)(work < num_sms ? work : num_sms);
-  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx>;
-  constexpr int kSmem = smem_bytes<kStats, Epi, ATx>();
+  if (kWRes && (g.n_tiles != 1 || K > 4 * BK || g.splits != 1)) {
+    set_error("gnnome_b200: W-resident GEMM needs one n tile, K <= 128, no split-K");
+    return GG_ERR_UNSUPPORTED;
+  }
+  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx, kWRes>;
+  constexpr int kSmem = smem_bytes<kStats, Epi, ATx, kWRes>();
+  static_assert(kSmem <= 227 * 1024, "shared-memory layout exceeds 227 KB");
   static bool attr_set = false;      // one static per template instantiation
   if (!attr_set) {
     GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
