@@ -11,7 +11,7 @@
 
 namespace gg {
 
-constexpr int kMlpThreads = 256;
+constexpr int kMlpThreads = 384;         // 12 warps: 3 per scheduler (the row loop is a chain of dependent FMAs / shuffles)
 constexpr int kMlpHid = 16, kMlpK = 4;       // hidden_edge_features = 16 (hyperparameters.py:11), edge_features 2 padded to 4
 
 template <int D>
@@ -22,22 +22,20 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
   constexpr int VPL = D / 32, H = kMlpHid;
   constexpr int kOut = D * H + D + H * kMlpK + H;            // dW2 | db2 | dW1 | db1
   __shared__ float red[kOut];
+  __shared__ __align__(16) float wsh[H * D];                 // W2 transposed: wsh[k][c], lane reads its channels as float4/float2
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kMlpThreads + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * kMlpThreads) >> 5;
   for (int i = threadIdx.x; i < kOut; i += kMlpThreads) red[i] = 0.f;
+  for (int i = threadIdx.x; i < D * H; i += kMlpThreads) wsh[(i % H) * D + i / H] = __ldg(W2 + i);   // W2[c][k] -> wsh[k][c]
+  __syncthreads();
 
-  float w[VPL][H], a2[VPL][H], ab2[VPL], a1[kMlpK], ab1 = 0.f;
+  float a2[VPL][H], ab2[VPL], a1[kMlpK], ab1 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int c = Row<D>::channel(i, lane);
     ab2[i] = 0.f;
 #pragma unroll
-    for (int k = 0; k < H; k += 4) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(W2 + (int64_t)c * H + k));
-      w[i][k] = x.x; w[i][k + 1] = x.y; w[i][k + 2] = x.z; w[i][k + 3] = x.w;
-      a2[i][k] = 0.f; a2[i][k + 1] = 0.f; a2[i][k + 2] = 0.f; a2[i][k + 3] = 0.f;
-    }
+    for (int k = 0; k < H; ++k) a2[i][k] = 0.f;
   }
 #pragma unroll
   for (int j = 0; j < kMlpK; ++j) a1[j] = 0.f;
@@ -68,11 +66,23 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
 #pragma unroll
     for (int k = 0; k < H; ++k) v[k] = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      ab2[i] += gr.v[i];
+    for (int i = 0; i < VPL; ++i) ab2[i] += gr.v[i];
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        v[k] = fmaf(gr.v[i], w[i][k], v[k]);                 // partial (g W2)[k] over this lane's channels
+    for (int k = 0; k < H; ++k) {
+      Row<D> wk;                                             // W2[c][k] for this lane's channels (conflict-free LDS)
+      if constexpr (D == 64) {
+        const float2 x = reinterpret_cast<const float2*>(wsh + k * D)[lane];
+        wk.v[0] = x.x; wk.v[1] = x.y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < D / 128; ++j) {
+          const float4 x = reinterpret_cast<const float4*>(wsh + k * D + 128 * j)[lane];
+          wk.v[4 * j] = x.x; wk.v[4 * j + 1] = x.y; wk.v[4 * j + 2] = x.z; wk.v[4 * j + 3] = x.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        v[k] = fmaf(gr.v[i], wk.v[i], v[k]);                 // partial (g W2)[k] over this lane's channels
         a2[i][k] = fmaf(gr.v[i], h[k], a2[i][k]);            // dW2[c][k] += g[c] hid[k]
       }
     }
