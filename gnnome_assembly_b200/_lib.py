@@ -74,6 +74,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        if os.environ.get("GG_DEBUG_FLAGS") is not None:  # experiment switches, see include/gnnome_b200.h
+            handle.gg_debug_flags(int(os.environ["GG_DEBUG_FLAGS"]))
         if os.environ.get("GG_TC_MODE") is not None:      # 0 = FFMA everywhere, 1 = tcgen05 3xTF32 where eligible
             handle.gg_set_tc_mode(int(os.environ["GG_TC_MODE"]))
     return _lib

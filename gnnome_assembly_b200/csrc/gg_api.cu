@@ -5,6 +5,7 @@
 #include "gg_gemm_ffma.cuh"
 #include "gg_gemm_tc.cuh"
 #include "gg_layer_kernels.cuh"
+#include "gg_layer_bulk.cuh"
 
 namespace gg {
 
@@ -133,10 +134,31 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
       rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
     if (rc) return rc;
   }
-  GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
-  edge_gate_fwd_kernel<D, NORM><<<node_grid(edge_gate_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
-      N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
-  GG_KERNEL_END("edge_gate_fwd_kernel", st);
+  if (E > 0 && (tc::tc_dbg_ref() & 8)) {
+    // gg_debug_flags(8): streamed operands staged through shared memory by bulk copies (gg_layer_bulk.cuh).
+    // Parity-green, but measured SLOWER than the register-staged kernel on the bench graph (154 vs 141 us at
+    // d = 128: 16 consumer warps per SM instead of 24, every row crosses shared memory), so it is not the default.
+    auto kern = edge_gate_fwd_bulk_kernel<D, NORM>;
+    constexpr int kSmem = 6 * kBulkStageBytes;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+      GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBulkThreads, kSmem) != cudaSuccess || occ < 1) occ = 1;
+      per_sm = occ;
+    }
+    int64_t blocks = (N + kBulkNodes - 1) / kBulkNodes;
+    if (blocks > (int64_t)sm_count() * per_sm) blocks = (int64_t)sm_count() * per_sm;
+    GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
+    kern<<<(unsigned)blocks, kBulkThreads, kSmem, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e,
+                                                        residual, e_out, agg);
+    GG_KERNEL_END("edge_gate_fwd_kernel", st);
+  } else {
+    GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
+    edge_gate_fwd_kernel<D, NORM><<<node_grid(edge_gate_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
+        N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
+    GG_KERNEL_END("edge_gate_fwd_kernel", st);
+  }
   GG_KERNEL_BEGIN("node_agg_fwd_kernel", st);
   node_agg_fwd_kernel<D, NORM><<<node_grid(node_agg_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
       N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D);

@@ -42,7 +42,9 @@ const char* gg_last_error(void);
  * gg_set_tc_mode(0): true-fp32 FFMA kernel everywhere.  Returns the previous mode. */
 int gg_set_tc_mode(int mode);
 /* experiment switches for the tensor-core GEMM epilogue (tools/epi_experiment.py): bit 0 skips the column
- * statistics, bit 1 skips the epilogue operand prefetch (WRONG RESULTS; timing experiments only). Returns old. */
+ * statistics, bit 1 skips the epilogue operand prefetch (WRONG RESULTS; timing experiments only); bit 3 (8) runs
+ * the forward edge-gate pass with its streamed operands staged through shared memory by cp.async.bulk (correct
+ * results; measured slower than the default register-staged kernel, kept as an experiment). Returns old. */
 int gg_debug_flags(int flags);
 int64_t gg_launch_count(void);
 int gg_profile_enable(int on);
