@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnnome_b200.so")
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(_HERE, "libgnnome_b200.so")     # GG_LIB: A/B builds of the same ABI
 
 _p = C.c_void_p
 _i = C.c_int

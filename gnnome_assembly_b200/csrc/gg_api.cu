@@ -39,6 +39,11 @@ static unsigned node_grid(Kern kern, int64_t n) {
 
 // 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
 static int g_tc_mode = 1;
+#ifdef GG_NO_WRES             // A/B builds: per-stage B operand everywhere
+#define GG_WRES(D) false
+#else
+#define GG_WRES(D) ((D) <= 128)
+#endif
 namespace tc { int& tc_dbg_ref() { static int v = 0; return v; } }
 
 static int pick_splits(int64_t K, int64_t tiles) {
@@ -128,7 +133,7 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     EpiEdgeGate epi{t, D, b3, P, pl->src, pl->dst};
     constexpr int BN = D >= 128 ? 128 : 64;
     if (g_tc_mode && tc::eligible(false, false, E, D, D, D, D, e_in, B3))
-      rc = tc::launch<false, false, NORM == GG_NORM_BATCH, false, EpiEdgeGate, tc::NoATx, (D <= 128)>(
+      rc = tc::launch<false, false, NORM == GG_NORM_BATCH, false, EpiEdgeGate, tc::NoATx, GG_WRES(D)>(
           "gemm_edge_gate", e_in, D, B3, D, E, D, D, 1, stats, nullptr, epi, sm_count(), st);
     else
       rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
@@ -200,7 +205,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   if (fused_gt) {
     EpiAddMaskT<true, false> epi{g_e_in, (int64_t)D, g_eo, nullptr};
     tc::BnBwdATx atx{stats, bstats + 2 * D, gamma_e, beta_e, 1.0 / (double)E, g_t, (int64_t)D};
-    rc = tc::launch<false, true, false, false, EpiAddMaskT<true, false>, tc::BnBwdATx, (D <= 128)>(
+    rc = tc::launch<false, true, false, false, EpiAddMaskT<true, false>, tc::BnBwdATx, GG_WRES(D)>(
         "gemm_bwd_e_in", g_eo, D, B3, D, E, D, D, 1, nullptr, nullptr, epi, sm_count(), st, atx, t);
     if (rc) return rc;
   } else {

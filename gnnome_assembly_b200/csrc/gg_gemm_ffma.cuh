@@ -337,7 +337,8 @@ struct EpiAtomic {
 struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
-  static constexpr bool kWideStaging = true;      // fused gathers + statistics: the epilogue is the longer side
+  static constexpr bool kWideStaging = false;     // d = 128 runs W-resident (16-column chunks); at d = 256 the wide tile
+                                                  // measured 3-4 % slower on the 1M-edge graph (same-box A/B, tools/ab_sweep.sh)
   static constexpr bool kRowReduce = false;
   struct PreD { float4 p1; };     // B1h[src]: random row gather -> a whole tile ahead
   struct PreN { float4 p2; };     // B2h[dst]: edges are dst-sorted, consecutive rows share it -> one chunk ahead

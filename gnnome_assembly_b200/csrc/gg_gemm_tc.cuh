@@ -48,10 +48,15 @@ constexpr int BAR_BYTES = 256;
 //   A transform: 3 stages that also hold the second streamed A tile = 3 x 64 KB; staging 2 x 8 KB
 template <class ATx, class Epi, bool kWRes = false>
 struct Cfg {
-  // wide staging pays where the epilogue is the longer side (fused gathers + statistics, plain stores of wide
-  // outputs): measured gemm_edge_gate 159 -> 154 us, gemm_node_proj 67 -> 63 us; the split-K weight gradients and
-  // the bwd-data GEMMs have long K loops and lose more from the fourth stage than they gain (79 -> 88 us)
+  // wide staging pays for plain stores of wide outputs and is required by the row-reducing score epilogue: measured
+  // gemm_node_proj 67 -> 61 us (gemm_edge_gate 159 -> 154 us at d = 128, where W-residency is used instead; at
+  // d = 256 it lost 3-4 % in a same-box A/B and is off); the split-K weight gradients and the bwd-data GEMMs have
+  // long K loops and lose more from the fourth stage than they gain (79 -> 88 us)
+#ifdef GG_NO_WIDE            // A/B builds (tools/ab_build.sh): the layout before the per-epilogue configuration
+  static constexpr bool kWide = !ATx::kActive && Epi::kRowReduce;      // (the row reduction needs the wide tile)
+#else
   static constexpr bool kWide = !ATx::kActive && Epi::kWideStaging && !kWRes;
+#endif
   // W-resident (kWRes): the whole B operand (a d x d weight, K <= 128: 4 K-blocks of B_hi and of B_lo = 128 KB)
   // is loaded and split ONCE per CTA; the ring then carries only A tiles.  The kernel is bound by the LSU /
   // shared-memory pipe (ncu: l1tex 66-70 % busy, everything else < 40 %), and per K-block the B side was 16 KB of
