@@ -132,7 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, dt, cores, sample = cpu_oracle_rate(args.steps, max(args.warmup, 1), scale=0.125)
+    val, dt, cores, sample = cpu_oracle_rate(args.steps, max(args.warmup, 1), scale=0.25)   # same sample as our arm's cpu_baseline
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,

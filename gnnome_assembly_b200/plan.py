@@ -92,6 +92,19 @@ class GraphPlan:
     def array(self, name):
         """Copy of one of the plan's device index arrays as an int32 torch tensor (cached)."""
         cache = self.__dict__.setdefault("_arrays", {})
+        slab = self.__dict__.get("_slab")
+        if name not in cache and slab is not None:
+            # sub-graph plan: the arrays ARE slices of the caller-owned slab (layout of gg_subplan_fill)
+            e1, n1 = max(self.num_edges, 1), self.num_nodes + 1
+            edge_order = ["src", "dst", "out_eid", "out_dst", "perm", "inv_perm", "parent_eid", "csrc", "cdst"]
+            node_order = ["in_ptr", "out_ptr", "node_perm", "node_inv"]
+            if name in edge_order:
+                off = edge_order.index(name) * e1
+                cache[name] = slab[off:off + self.num_edges]
+            else:
+                off = len(edge_order) * e1 + node_order.index(name) * n1
+                n = n1 if name in ("in_ptr", "out_ptr") else self.num_nodes
+                cache[name] = slab[off:off + n]
         if name not in cache:
             which = self._WHICH[name]
             n = (self.num_nodes + 1 if name in ("in_ptr", "out_ptr")
