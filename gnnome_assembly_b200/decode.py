@@ -1,4 +1,5 @@
-"""Greedy contig decoding on the GPU — SURVEY.md §8f row 4; drop-in for inference.py:182-259 (`get_contigs`).
+"""Greedy contig decoding on the GPU — SURVEY.md §8f row 4; drop-in for inference.py:182-259 (`get_contigs`)
+and inference.py:80-180 (`get_contigs_baselines`).
 
     walks = get_contigs(g, succs, preds, edges, nb_paths, len_threshold, device)      # inference.py:369 / :487
 
@@ -150,24 +151,22 @@ def sample_edges(dg, scores, visited, nb_paths, generator=None):
     return torch.searchsorted(cdf, u, right=True).clamp_(max=dg.num_edges - 1)
 
 
-def get_contigs(g, succs, preds, edges, nb_paths=50, len_threshold=20, device="cpu", start_edges=None, scores=None,
-                generator=None):
-    """Drop-in for inference.py:182-259.  Returns the list of contigs, each a list of node ids.
-    start_edges: optional iterable of per-iteration (src_ids, dst_ids) sequences replacing the random draw.
-    scores: optional per-edge tensor to walk on instead of g.edata['score'] (the overlap-length / similarity
-    baselines of get_contigs_baselines, inference.py:134-141)."""
-    score_t = g.edata["score"] if scores is None else scores
-    dev = _cuda_device(device, score_t)
+def _decode_loop(g, succs, preds, edges, nb_paths, len_threshold, device, start_edges, score_list, generator):
+    """The iteration of inference.py:182-259 / :80-180.  score_list[0] drives sampling, the choice of the best
+    walk and the visited set; the other score arrays (the baselines of :134-141) are walked from the same start
+    edges and reported at the chosen index."""
+    dev = _cuda_device(device, *score_list)
     src, dst = g.edges()
     N = int(g.num_nodes())
     dg = DecodeGraph(src, dst, N, dev, succs, preds, edges)
     with torch.cuda.device(dev):
-        score_d = torch.as_tensor(score_t).reshape(-1).to(dev, torch.float32).contiguous()
+        scores_d = [torch.as_tensor(t).reshape(-1).to(dev, torch.float32).contiguous() for t in score_list]
         prefix = torch.as_tensor(g.edata["prefix_length"]).reshape(-1).to(dev, torch.int64).contiguous()
         rlen = torch.as_tensor(g.ndata["read_length"]).reshape(-1).to(dev, torch.int64).contiguous()
         visited = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
         starts = iter(start_edges) if start_edges is not None else None
-        all_contigs, wb = [], None
+        results = [[] for _ in score_list]
+        batches = [None] * len(score_list)
         while True:
             if starts is not None:
                 try:
@@ -178,19 +177,43 @@ def get_contigs(g, succs, preds, edges, nb_paths=50, len_threshold=20, device="c
                 s_t = torch.as_tensor(np.asarray(s_list), dtype=torch.int32).to(dev)
                 d_t = torch.as_tensor(np.asarray(d_list), dtype=torch.int32).to(dev)
             else:
-                idx = sample_edges(dg, score_d, visited, nb_paths, generator)
+                idx = sample_edges(dg, scores_d[0], visited, nb_paths, generator)
                 if idx is None:
                     break
                 eid = dg.canon_eid[idx]
                 s_t, d_t = dg.src[idx], dg.dst[idx]
-            wb = decode_walks(dg, score_d, prefix, rlen, visited, s_t, d_t, eid, out=wb)
-            beg, length, seq_len, err = wb.host()
+            for k, sc in enumerate(scores_d):
+                batches[k] = decode_walks(dg, sc, prefix, rlen, visited, s_t, d_t, eid, out=batches[k])
+            beg, length, seq_len, err = batches[0].host()
             if err:
                 raise RuntimeError("decode: a greedy walk ran into a cycle of single-neighbour nodes "
                                    "(the reference's walk_forwards / walk_backwards would not terminate)")
             best = int(np.argmax(seq_len))                         # max(all_walks, key=get_contig_length): first maximum
-            if int(length[best]) < len_threshold:                  # inference.py:243-244
+            if int(length[best]) < len_threshold:                  # inference.py:243-244 / :164-165
                 break
-            all_contigs.append(wb.walk(best, int(beg[best]), int(length[best])).cpu().tolist())
-            commit_walk(dg, wb, best, int(beg[best]), int(length[best]), visited)
-    return all_contigs
+            results[0].append(batches[0].walk(best, int(beg[best]), int(length[best])).cpu().tolist())
+            for k in range(1, len(scores_d)):
+                bk, lk, _, errk = batches[k].host()
+                if errk:
+                    raise RuntimeError("decode: a baseline walk ran into a cycle of single-neighbour nodes")
+                results[k].append(batches[k].walk(best, int(bk[best]), int(lk[best])).cpu().tolist())
+            commit_walk(dg, batches[0], best, int(beg[best]), int(length[best]), visited)
+    return results
+
+
+def get_contigs(g, succs, preds, edges, nb_paths=50, len_threshold=20, device="cpu", start_edges=None, scores=None,
+                generator=None):
+    """Drop-in for inference.py:182-259.  Returns the list of contigs, each a list of node ids.
+    start_edges: optional iterable of per-iteration (src_ids, dst_ids) sequences replacing the random draw.
+    scores: optional per-edge tensor to walk on instead of g.edata['score']."""
+    score_t = g.edata["score"] if scores is None else scores
+    return _decode_loop(g, succs, preds, edges, nb_paths, len_threshold, device, start_edges, [score_t], generator)[0]
+
+
+def get_contigs_baselines(g, succs, preds, edges, nb_paths=50, len_threshold=20, device="cpu", start_edges=None,
+                          generator=None):
+    """Drop-in for inference.py:80-180: besides the model's walks, the greedy walks on overlap length and on
+    overlap similarity from the same start edges.  Returns (all_contigs, all_contigs_len, all_contigs_sim)."""
+    res = _decode_loop(g, succs, preds, edges, nb_paths, len_threshold, device, start_edges,
+                       [g.edata["score"], g.edata["overlap_length"], g.edata["overlap_similarity"]], generator)
+    return res[0], res[1], res[2]

@@ -70,6 +70,29 @@ def get_contigs(scores, prefix_length, read_length, succs, preds, edge_id, start
     return contigs, visited
 
 
+def get_contigs_baselines(score_list, prefix_length, read_length, succs, preds, edge_id, start_edges, len_threshold=20):
+    """inference.py:80-180: score_list = [model scores, overlap_length, overlap_similarity]; the model's walks choose
+    the contig and the visited set (:146-158,172), the two baselines are walked from the same start edges (:134-141)
+    and reported at the chosen index (:175-178).  Returns three lists of walks."""
+    out, visited = [[] for _ in score_list], set()
+    for starts in start_edges:
+        pairs = list(zip(*starts))
+        per_score = [walks_for_starts(pairs, sc, succs, preds, edge_id, visited) for sc in score_list]
+        walks, visiteds = per_score[0]
+        lengths = [contig_length(w, prefix_length, read_length, edge_id) for w in walks]
+        best = int(np.argmax(lengths))
+        walk, seen = walks[best], set(visiteds[best])
+        for a, b in zip(walk[:-1], walk[1:]):
+            t = set(succs[a]) & set(preds[b])
+            seen |= t | {x ^ 1 for x in t}
+        if len(walk) < len_threshold:
+            break
+        for k in range(len(score_list)):
+            out[k].append(per_score[k][0][best])
+        visited |= seen
+    return out
+
+
 def adjacency(src, dst, num_nodes):
     """graph_parser.py:12-73: successor / predecessor lists and the edge dictionary, filled in edge-id order."""
     succs = {i: [] for i in range(num_nodes)}

@@ -85,8 +85,25 @@ def run_case(name, seed, genome_lens, nb_paths, len_threshold, noise):
     inference.get_subgraph, inference.sample_edges = get_subgraph, sample_edges
     torch.manual_seed(seed)
     contigs = inference.get_contigs(g, succs, preds, edges, nb_paths=nb_paths, len_threshold=len_threshold, device="cpu")
+    # the baselines entry point (inference.py:80-180): model walks + overlap-length / overlap-similarity walks
+    drawn_main, drawn_b = list(drawn), []
+    drawn.clear()
+    base = None
+    for attempt in range(20):                             # a draw that exhausts the graph makes the reference raise
+        drawn.clear()                                     # (Categorical over zero edges): take the first seed that ends
+        torch.manual_seed(seed + 1000 + attempt)          # through the length threshold
+        try:
+            base = inference.get_contigs_baselines(g, succs, preds, edges, nb_paths=nb_paths, len_threshold=len_threshold, device="cpu")
+            break
+        except ValueError:
+            continue
+    assert base is not None
+    drawn_b = list(drawn)
+    drawn[:] = drawn_main
     inference.get_subgraph, inference.sample_edges = ref_get_subgraph, ref_sample_edges
-    torch.save({"seed": seed, "genome_lens": list(genome_lens), "src": gs.src, "dst": gs.dst,
+    torch.save({"baselines": {"start_edges": drawn_b, "contigs": base[0], "contigs_len": base[1], "contigs_sim": base[2]},
+                "overlap_length": gs.overlap_length, "overlap_similarity": gs.overlap_similarity,
+                "seed": seed, "genome_lens": list(genome_lens), "src": gs.src, "dst": gs.dst,
                 "prefix_length": gs.prefix_length, "read_length": gs.read_length, "nb_paths": nb_paths, "len_threshold": len_threshold,
                 "score": score, "start_edges": drawn, "contigs": contigs,
                 "num_nodes": gs.num_nodes, "num_edges": gs.num_edges}, os.path.join(HERE, name + ".pt"))

@@ -26,6 +26,16 @@ def test_oracle_reproduces_reference_contigs(name):
     assert contigs == g["contigs"]
 
 
+@pytest.mark.parametrize("name", ["ref_decode_small", "ref_decode_asm"])
+def test_oracle_reproduces_reference_baselines(name):
+    g = _gold(name)
+    b = g["baselines"]
+    succs, preds, edge_id = do.adjacency(g["src"], g["dst"], g["num_nodes"])
+    got = do.get_contigs_baselines([g["score"], g["overlap_length"], g["overlap_similarity"]], g["prefix_length"],
+                                   g["read_length"], succs, preds, edge_id, b["start_edges"], g["len_threshold"])
+    assert got[0] == b["contigs"] and got[1] == b["contigs_len"] and got[2] == b["contigs_sim"]
+
+
 def test_oracle_walk_semantics_small():
     # 0 -> 2 -> 4 -> 6 with a tempting branch 2 -> 8 (higher score) that is already visited
     src = np.array([0, 2, 2, 4]); dst = np.array([2, 4, 8, 6])
@@ -73,6 +83,21 @@ def test_gpu_get_contigs_matches_reference_golden(name, with_dicts):
     contigs = get_contigs(g, succs, preds, edges, gold["nb_paths"], gold["len_threshold"], device="cpu",
                           start_edges=gold["start_edges"])
     assert contigs == gold["contigs"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_decode_small", "ref_decode_asm"])
+def test_gpu_get_contigs_baselines_matches_reference_golden(name):
+    _dev()
+    from gnnome_assembly_b200.decode import get_contigs_baselines
+    gold = _gold(name)
+    b = gold["baselines"]
+    g = _graph(gold, gold["score"])
+    g.edata["overlap_length"] = torch.from_numpy(np.asarray(gold["overlap_length"], dtype=np.float32))
+    g.edata["overlap_similarity"] = torch.from_numpy(np.asarray(gold["overlap_similarity"], dtype=np.float32))
+    got = get_contigs_baselines(g, None, None, None, gold["nb_paths"], gold["len_threshold"], device="cpu",
+                                start_edges=b["start_edges"])
+    assert got[0] == b["contigs"] and got[1] == b["contigs_len"] and got[2] == b["contigs_sim"]
 
 
 @pytest.mark.gpu
