@@ -103,7 +103,9 @@ static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const flo
   const int64_t m_tiles = (N + kBM - 1) / kBM;
   if (g_tc_mode && tc::eligible(true, true, N, K, M, lddy, ldx, dY, X)) {
     const int64_t tiles = m_tiles * (K / tc::BN);
-    int64_t want = (sm_count() + tiles - 1) / tiles;
+    // persistent CTAs, one work item (tile x split) at a time: the items must fit ONE wave.  Rounding the split count
+    // up (5 tiles x 30 splits = 150 items on 148 SMs) made two CTAs run a second item while 146 idled: floor.
+    int64_t want = sm_count() / tiles;
     const int64_t max_by_k = (M + 1023) / 1024;
     if (want > max_by_k) want = max_by_k;
     if (want < 1) want = 1;
