@@ -39,41 +39,57 @@ def _cuda_device(device, *tensors):
     return torch.device("cuda", torch.cuda.current_device())     # inference.py passes device='cpu' to get_contigs
 
 
+def adjacency_arrays(src, dst, num_nodes):
+    """(succ_ptr, succ_node, succ_eid, pred_ptr, pred_node, pred_eid, canon_eid) as int64 tensors on src's device.
+    The reference fills its successor / predecessor lists by one pass over graph.edges() in edge-id order
+    (graph_parser.py:27-29, :48-50) = a stable sort of the edge ids by src resp. dst.  It looks edges up through a
+    {(src, dst): id} dictionary (graph_parser.py:69-72): of parallel edges only the LAST id is ever seen — scores and
+    prefix lengths are read through that id (canon_eid)."""
+    n, E = int(num_nodes), int(src.numel())
+    if E and bool((src == dst).any()):
+        raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
+    ids = torch.arange(E, device=src.device, dtype=torch.int64)
+    if E:
+        _, inv = torch.unique(src * max(n, 1) + dst, return_inverse=True)
+        last = torch.zeros(int(inv.max()) + 1, dtype=torch.int64, device=src.device).scatter_reduce_(0, inv, ids, "amax")
+        canon = last[inv]
+    else:
+        canon = ids
+    out = []
+    for key, other in ((src, dst), (dst, src)):
+        order = torch.argsort(key, stable=True)
+        ptr_ = torch.zeros(n + 1, dtype=torch.int64, device=src.device)
+        ptr_[1:] = torch.cumsum(torch.bincount(key, minlength=n), 0)
+        out += [ptr_, other[order], canon[order]]
+    return (*out, canon)
+
+
 class DecodeGraph:
     """Successor / predecessor lists as device CSR in caller node ids, list order = the reference's."""
 
     def __init__(self, src, dst, num_nodes, device, succs=None, preds=None, edges=None):
         self.device = torch.device(device)
         self.num_nodes = int(num_nodes)
-        src = torch.as_tensor(src).to(torch.int64).cpu().numpy()
-        dst = torch.as_tensor(dst).to(torch.int64).cpu().numpy()
-        self.num_edges = int(src.size)
-        if np.any(src == dst):
-            raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
-        # the reference looks edges up through a {(src, dst): id} dictionary (graph_parser.py:69-72): of parallel
-        # edges only the LAST id is ever seen — scores and prefix lengths are read through that id
-        key = src * max(self.num_nodes, 1) + dst
-        _, inv = np.unique(key, return_inverse=True)
-        last = np.full(inv.max() + 1 if inv.size else 0, -1, dtype=np.int64)
-        np.maximum.at(last, inv, np.arange(src.size))
-        canon = last[inv] if inv.size else np.zeros(0, dtype=np.int64)
+        src_t = torch.as_tensor(src).reshape(-1).to(torch.int64)
+        dst_t = torch.as_tensor(dst).reshape(-1).to(torch.int64)
+        self.num_edges = int(src_t.numel())
+        self._src_t, self._dst_t = src_t, dst_t
+        self._edge_of = None
         if succs is None or preds is None:
-            # graph_parser.py:27-29, :48-50: lists are filled by one pass over graph.edges() in edge-id order
-            s_ord = np.argsort(src, kind="stable")
-            p_ord = np.argsort(dst, kind="stable")
-            s_node, p_node = dst[s_ord], src[p_ord]
-            s_eid, p_eid = canon[s_ord], canon[p_ord]
-            s_ptr = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=self.num_nodes))])
-            p_ptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=self.num_nodes))])
+            arrays = adjacency_arrays(src_t.to(self.device), dst_t.to(self.device), self.num_nodes)
         else:
+            src_np, dst_np = src_t.cpu().numpy(), dst_t.cpu().numpy()
+            if np.any(src_np == dst_np):
+                raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
             s_ptr, s_node, s_eid = self._from_dict(succs, edges, forward=True)
             p_ptr, p_node, p_eid = self._from_dict(preds, edges, forward=False)
-        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
-        self.succ_ptr, self.succ_node, self.succ_eid = i32(s_ptr), i32(s_node), i32(s_eid)
-        self.pred_ptr, self.pred_node, self.pred_eid = i32(p_ptr), i32(p_node), i32(p_eid)
-        self.src, self.dst, self.canon_eid = i32(src), i32(dst), i32(canon)
-        self._edge_of = None
-        self._src_np, self._dst_np = src, dst
+            canon = np.array([edges[(int(a), int(b))] for a, b in zip(src_np, dst_np)], dtype=np.int64)
+            arrays = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)) for a in
+                      (s_ptr, s_node, s_eid, p_ptr, p_node, p_eid, canon)]
+        i32 = lambda a: a.to(self.device, torch.int32).contiguous()
+        (self.succ_ptr, self.succ_node, self.succ_eid, self.pred_ptr, self.pred_node, self.pred_eid,
+         self.canon_eid) = (i32(a) for a in arrays)
+        self.src, self.dst = i32(src_t), i32(dst_t)
 
     def _from_dict(self, adj, edges, forward):
         if edges is None:
@@ -88,7 +104,8 @@ class DecodeGraph:
 
     def edge_id(self, s, d):
         if self._edge_of is None:
-            self._edge_of = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(self._src_np, self._dst_np))}
+            a, b = self._src_t.cpu().tolist(), self._dst_t.cpu().tolist()
+            self._edge_of = {(u, v): i for i, (u, v) in enumerate(zip(a, b))}      # last id of a parallel pair wins
         return self._edge_of[(int(s), int(d))]
 
 

@@ -36,6 +36,26 @@ def test_oracle_reproduces_reference_baselines(name):
     assert got[0] == b["contigs"] and got[1] == b["contigs_len"] and got[2] == b["contigs_sim"]
 
 
+@pytest.mark.parametrize("n,m", [(1, 0), (6, 9), (50, 400), (300, 5000)])
+def test_adjacency_arrays_match_reference_dictionaries(n, m):
+    """host logic of the decoder (device-agnostic torch code, run on the CPU here): CSR lists in the order of the
+    reference's dictionaries, parallel edges resolved to the last id like the reference's {(src,dst): id} lookup"""
+    from gnnome_assembly_b200.decode import adjacency_arrays
+    rng = np.random.default_rng(n + m)
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    sp, sn, se, pp, pn, pe, canon = [a.numpy() for a in adjacency_arrays(torch.from_numpy(src), torch.from_numpy(dst), n)]
+    succs, preds, eid = do.adjacency(src, dst, n)
+    for u in range(n):
+        assert sn[sp[u]:sp[u + 1]].tolist() == succs[u] and pn[pp[u]:pp[u + 1]].tolist() == preds[u]
+        assert se[sp[u]:sp[u + 1]].tolist() == [eid[(u, v)] for v in succs[u]]
+        assert pe[pp[u]:pp[u + 1]].tolist() == [eid[(v, u)] for v in preds[u]]
+    assert canon.tolist() == [eid[(a, b)] for a, b in zip(src.tolist(), dst.tolist())]
+    with pytest.raises(ValueError, match="self loops"):
+        adjacency_arrays(torch.tensor([0, 1]), torch.tensor([1, 1]), 2)
+
+
 def test_oracle_walk_semantics_small():
     # 0 -> 2 -> 4 -> 6 with a tempting branch 2 -> 8 (higher score) that is already visited
     src = np.array([0, 2, 2, 4]); dst = np.array([2, 4, 8, 6])
