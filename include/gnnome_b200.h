@@ -53,9 +53,11 @@ int gg_profile_report(char* buf, size_t cap);
 /* ---- graph plan -------------------------------------------------------------------------
  * Replaces the structure side of the DGLGraph argument of GraphGatedGCNModel.forward
  * (models/full_graph.py:22) and dgl.reverse (layers/gated_gcn_full.py:115).
- * src/dst: int32[E] in the caller's edge-id order, HOST or DEVICE memory.  Builds, on the device,
- * the internal edge order (stable sort by dst = CSR over in-edges) and a CSR over out-edges that
- * points into it.  Internal position p holds caller edge perm[p]. */
+ * src/dst: int32[E] in the caller's edge-id order, HOST or DEVICE memory.  Builds the internal edge order
+ * (stable sort by dst = CSR over in-edges) and a CSR over out-edges that points into it, once per graph, on
+ * the host (counting sort + breadth-first relabelling, ~27 ms for a chr19 graph) and uploads the arrays as one
+ * library-owned device allocation; synchronises `stream`.  Internal position p holds caller edge perm[p].
+ * (Per-batch sub-graph plans are built on the device: gg_subplan_* below.) */
 int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
                    void* stream, gg_plan_t** out);
 /* flags: GG_PLAN_RELABEL (default of gg_plan_create) renumbers the nodes breadth-first so that the
