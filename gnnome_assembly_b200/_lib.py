@@ -21,6 +21,7 @@ SIGNATURES = {
     "gg_last_error": (C.c_char_p, []),
     "gg_set_tc_mode": (_i, [_i]),
     "gg_debug_flags": (_i, [_i]),
+    "gg_debug_trace": (_i, [_p, _i, _i]),
     "gg_launch_count": (_i64, []),
     "gg_profile_enable": (_i, [_i]),
     "gg_profile_report": (_i, [C.c_char_p, C.c_size_t]),

@@ -323,6 +323,19 @@ extern "C" {
 
 int gg_debug_flags(int flags) { const int old = tc::tc_dbg_ref(); tc::tc_dbg_ref() = flags; return old; }
 
+int gg_debug_trace(unsigned long long* out, int n, int reset) {
+  GG_REQUIRE(out != nullptr && n >= 0, "debug_trace: bad arguments");
+  unsigned long long host[tc::TR_SLOTS] = {};
+  GG_CUDA(cudaDeviceSynchronize());
+  GG_CUDA(cudaMemcpyFromSymbol(host, tc::gg_tc_trace, sizeof host));
+  for (int i = 0; i < n; ++i) out[i] = i < (int)tc::TR_SLOTS ? host[i] : 0ull;
+  if (reset) {
+    unsigned long long zero[tc::TR_SLOTS] = {};
+    GG_CUDA(cudaMemcpyToSymbol(tc::gg_tc_trace, zero, sizeof zero));
+  }
+  return GG_OK;
+}
+
 int gg_set_tc_mode(int mode) {
   const int old = g_tc_mode;
   g_tc_mode = mode ? 1 : 0;

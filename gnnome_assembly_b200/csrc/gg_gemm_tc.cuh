@@ -83,6 +83,28 @@ constexpr int TMEM_A0 = 256;
 
 int& tc_dbg_ref();                                // experiment switches, see Args::dbg
 
+// ---------------------------------------------------------------------------------- role tracing (-DGG_TC_TRACE)
+// Where does a tile's time go?  ncu's stall sampling cannot tell a role that waits from a role that works slowly.
+// A trace build (tools/ab_build.sh trace "-DGG_TC_TRACE", tools/tc_trace.py) accumulates, per role, the clock64
+// cycles spent inside each mbarrier wait and in total, summed over CTAs into gg_tc_trace[] (read and reset through
+// gg_debug_trace).  In the default build every call below is empty.
+#ifdef GG_TC_TRACE
+constexpr bool kTrace = true;
+#else
+constexpr bool kTrace = false;
+#endif
+enum TraceSlot { TR_PROD_WAIT_EMPTY = 0, TR_PROD_TOTAL, TR_MMA_WAIT_AB, TR_MMA_WAIT_ACC, TR_MMA_TOTAL, TR_CONV_WAIT_RAW,
+                 TR_CONV_TOTAL, TR_EPI_WAIT_ACC, TR_EPI_CHUNKS, TR_EPI_FETCH, TR_EPI_TOTAL, TR_CTAS, TR_TILES, TR_SLOTS };
+__device__ unsigned long long gg_tc_trace[TR_SLOTS];      // this header is compiled into exactly one translation unit (gg_api.cu)
+struct Tracer {
+  unsigned long long t0 = 0, t_role = 0;
+  __device__ __forceinline__ void role_begin() { if constexpr (kTrace) t_role = clock64(); }
+  __device__ __forceinline__ void role_end(int slot) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], clock64() - t_role); }
+  __device__ __forceinline__ void begin() { if constexpr (kTrace) t0 = clock64(); }
+  __device__ __forceinline__ void end(int slot) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], clock64() - t0); }
+  __device__ __forceinline__ void count(int slot, unsigned long long n) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], n); }
+};
+
 struct Args {
   int64_t M; int N; int64_t K;
   int m_tiles, n_tiles, splits;
@@ -361,6 +383,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
       // ================================================================ TMA producer
       int s = 0; uint32_t ph = 0;
+      Tracer tr;
+      tr.role_begin();
+      tr.count(TR_CTAS, 1);
       if constexpr (kWRes) {
         if (blockIdx.x < total_work) {
           mbar_expect_tx(bres_full, (uint32_t)nkb_total * TILE_BYTES);
@@ -378,7 +403,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
         for (int kb = 0; kb < nkb; ++kb) {
+          tr.begin();
           mbar_wait(empty(s), ph ^ 1u);
+          tr.end(TR_PROD_WAIT_EMPTY);
           const uint32_t st = stage0 + s * kStageBytes;
           mbar_expect_tx(full_raw(s), (Cfg<ATx, Epi, kWRes>::kATiles + (kWRes ? 0 : 1)) * TILE_BYTES);
           if constexpr (ATx::kActive) tma_load_2d(st + kOffA2, &tmA2, full_raw(s), (int)(kbeg + (int64_t)kb * BK), mt * BM);
@@ -399,22 +426,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
+        tr.count(TR_TILES, 1);
       }
+      tr.role_end(TR_PROD_TOTAL);
     } else if (warp == 1 && lane == 0) {
       // ================================================================ MMA issuer (one thread)
       constexpr uint32_t idesc = make_idesc(false, B_MN);          // A comes from TMEM: always K-major there
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+      Tracer tr;
+      tr.role_begin();
       if constexpr (kWRes) {
         if (blockIdx.x < total_work) { mbar_wait(bres_ready, 0u); tc_fence_after(); }
       }
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+        tr.begin();
         mbar_wait(tmem_empty(acc), acc_ph ^ 1u);
+        tr.end(TR_MMA_WAIT_ACC);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
+          tr.begin();
           mbar_wait(full_ab(s), ph);
+          tr.end(TR_MMA_WAIT_AB);
           tc_fence_after();
           const uint32_t st = stage0 + s * kStageBytes;
           const uint32_t a_hi = tmem_base + (uint32_t)(TMEM_A0 + 64 * s), a_lo = a_hi + 32;
@@ -434,6 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(tmem_full(acc));                   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
+      tr.role_end(TR_MMA_TOTAL);
     }
   } else if (ATx::kActive && warp < kEpiWarp0) {
     // ================================================================ converter with an A transform
@@ -446,13 +482,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int half = cw >> 2;
       const uint32_t lane_base = (uint32_t)(32 * (cw & 3)) << 16;
       int s = 0; uint32_t ph = 0;
+      Tracer tr;
+      const bool tr_on = kTrace && ct == 0;
+      if (tr_on) tr.role_begin();
       if constexpr (kWRes) split_resident_b(ct);
       for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, sp; decode(w, mt, nt, sp);
         int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
         const int64_t m = (int64_t)mt * BM + t;
         for (int kb = 0; kb < nkb; ++kb) {
+          if (tr_on) tr.begin();
           mbar_wait(full_raw(s), ph);
+          if (tr_on) tr.end(TR_CONV_WAIT_RAW);
           const uint8_t* st = gen + s * kStageBytes;
           // g_eo[row, c0 + 16 half ..+15] (tile 0) and t (tile 3) -> g_t (stored, and the A operand)
           const float4* row = reinterpret_cast<const float4*>(st + t * 128);
@@ -509,6 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
+      if (tr_on) tr.role_end(TR_CONV_TOTAL);
     }
   } else if (!ATx::kActive && warp < 8) {
     // ================================================================ converter (128 threads, thread = A row)
@@ -516,13 +558,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     int s = 0; uint32_t ph = 0;
+    Tracer tr;
+    const bool tr_on = kTrace && t == 0;
+    if (tr_on) tr.role_begin();
     if constexpr (kWRes) split_resident_b(t);
     for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, sp; decode(w, mt, nt, sp);
       int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
       float bsum = 0.f;
       for (int kb = 0; kb < nkb; ++kb) {
+        if (tr_on) tr.begin();
         mbar_wait(full_raw(s), ph);
+        if (tr_on) tr.end(TR_CONV_WAIT_RAW);
         const uint8_t* st = gen + s * kStageBytes;
         // ---- A row t of this K-block -> registers (k order), hi = raw bits, lo = x - trunc(x)
         uint32_t hi[32], lo[32];
@@ -580,6 +627,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (g.bias_grad != nullptr && nt == 0 && m < g.M) atomicAdd(g.bias_grad + m, bsum);
       }
     }
+    if (tr_on) tr.role_end(TR_CONV_TOTAL);
   } else {
     // ================================================================ epilogue (2 groups x 128 threads)
     // group grp owns accumulator columns [64 grp, 64 grp + 64), 4 chunks of 16 columns.  Per chunk: every
@@ -642,6 +690,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (Epi::kIdx) { idx_base[buf * 2 * BM + tg] = sv; idx_base[buf * 2 * BM + BM + tg] = dv; }
     };
 
+    Tracer tr;
+    const bool tr_on = kTrace && tg == 0 && grp == 0;
+    if (tr_on) tr.role_begin();
     int acc = 0; uint32_t acc_ph = 0;
     int cur = 0;                                        // idx buffer of the current tile
     int64_t w = blockIdx.x;
@@ -662,7 +713,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (; w < total_work; w += gridDim.x) {
       const int64_t wn = w + gridDim.x, wnn = wn + gridDim.x;
       const bool has_next = wn < total_work;
+      if (tr_on) tr.begin();
       mbar_wait(tmem_full(acc), acc_ph);
+      if (tr_on) { tr.end(TR_EPI_WAIT_ACC); tr.begin(); }
       tc_fence_after();
       const int64_t m0 = (int64_t)mt * BM;
 #pragma unroll
@@ -739,6 +792,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n < g.N) { atomicAdd(g.col_stats + n, a); atomicAdd(g.col_stats + g.N + n, b); }
         }
       }
+      if (tr_on) { tr.end(TR_EPI_CHUNKS); tr.begin(); }
       // one batch: every operand of the next tile, then the node ids of the tile after it
       if (has_next) fetch_tile(mtn, ntn, cur ^ 1);
       int mtt = 0, ntt = 0, spt = 0;
@@ -753,7 +807,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mtn = mtt; ntn = ntt; spn = spt;
       cur ^= 1;
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      if (tr_on) tr.end(TR_EPI_FETCH);
     }
+    if (tr_on) tr.role_end(TR_EPI_TOTAL);
   }
 
   tc_fence_before();

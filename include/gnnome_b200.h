@@ -46,6 +46,10 @@ int gg_set_tc_mode(int mode);
  * the forward edge-gate pass with its streamed operands staged through shared memory by cp.async.bulk (correct
  * results; measured slower than the default register-staged kernel, kept as an experiment). Returns old. */
 int gg_debug_flags(int flags);
+/* Trace builds only (-DGG_TC_TRACE, tools/ab_build.sh + tools/tc_trace.py): per-role clock64 totals of the tcgen05
+ * GEMM (cycles inside each mbarrier wait / per role), summed over CTAs since the last reset; synchronises the
+ * device.  A default build returns zeros.  Slot order: gg_gemm_tc.cuh, enum TraceSlot. */
+int gg_debug_trace(unsigned long long* out, int n, int reset);
 int64_t gg_launch_count(void);
 int gg_profile_enable(int on);
 int gg_profile_report(char* buf, size_t cap);
