@@ -125,6 +125,7 @@ def cpu_oracle_rate(steps, warmup, scale):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     sample = (f"chr19-like graph at {scale:g}x genome length (N={g.num_nodes}, E={g.num_edges}), L={L} d={D} "
               f"fwd+bwd+Adam, {steps} timed steps after {warmup} warm-up")
+    cpu_oracle_rate.last_graph = (g.num_nodes, g.num_edges)
     return g.num_edges / dt, dt, torch.get_num_threads(), sample
 
 
@@ -166,14 +167,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, dt, cores, sample = cpu_oracle_rate(args.steps, max(args.warmup, 1), scale=0.25)   # same sample as our arm's cpu_baseline
+    # SAME config as our arm: the full configs[1] graph (seed 0, E = 372,650), same model, same step.  One CPU step is
+    # a few seconds on the box's host cores, so the driver's --steps 20 --warmup 5 run ends within a few minutes.
+    val, dt, cores, sample = cpu_oracle_rate(args.steps, max(args.warmup, 1), scale=1.0)
+    g_nodes, g_edges = cpu_oracle_rate.last_graph
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 8-layer GatedGCN d=128 fwd+bwd(+Adam) on a chr19-like assembly graph",
-                   "layers": L, "hidden": D, "norm": "batch", "note": "CPU oracle (pure-PyTorch restatement of the "
-                   "reference forward; DGL not installable), bounded sample"},
+                   "layers": L, "hidden": D, "norm": "batch", "nodes": g_nodes, "edges": g_edges,
+                   "note": "CPU oracle (pure-PyTorch restatement of the reference forward; DGL not installable) on the "
+                   "same graph, model and step as the engine arm"},
         "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -265,6 +270,31 @@ def run_ours(args):
             bucket.allreduce_mean(active=True)
         opt.step()
         return loss
+
+    # ---- parity gate (rank 0, N = 1): the FIRST step's loss and every parameter gradient against the CPU oracle on
+    # the same seed, graph and weights — the numbers timed below come from a path that is checked in this very run
+    parity = None
+    if world == 1 and not args.no_parity_check:
+        from oracle.gatedgcn_oracle import OracleModel, grads_close
+        from oracle.gatedgcn_oracle import bce_loss as oracle_bce
+        oracle = OracleModel(1, 2, D, HID_E, L, HID_S, True, NB_PE)
+        oracle.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+        torch.set_num_threads(os.cpu_count() or 1)
+        loss0 = bce_loss(model(graph, None, d_e, d_pe), d_y)
+        opt.zero_grad(set_to_none=True)
+        loss0.backward()
+        src64, dst64 = torch.from_numpy(g.src.astype(np.int64)), torch.from_numpy(g.dst.astype(np.int64))
+        ref0 = oracle_bce(oracle(src64, dst64, N, torch.from_numpy(g.e), torch.from_numpy(g.pe)), torch.from_numpy(g.y), POS_WEIGHT)
+        ref0.backward()
+        bad = grads_close({k: p.grad for k, p in model.named_parameters()},
+                          {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5)
+        parity = {"first_step_loss": float(loss0), "oracle_loss": float(ref0), "abs_diff": abs(float(loss0) - float(ref0)),
+                  "grad_tensors_checked": len(list(oracle.parameters())), "grad_mismatches": len(bad),
+                  "tolerance": "loss 1e-5 relative; gradients rtol 2e-3 of each tensor's max + 1e-5 of the model's max"}
+        assert parity["abs_diff"] < 1e-5 * max(1.0, abs(float(ref0))), f"bench: first-step loss differs from the oracle: {parity}"
+        assert not bad, f"bench: gradients differ from the oracle: {bad[:3]}"
+        opt.zero_grad(set_to_none=True)
+        del oracle
 
     graphed = None
     launches_per_step = None
@@ -382,12 +412,15 @@ def run_ours(args):
                     traffic, traffic_src = rec["dram_bytes_per_launch"], "profiles/r1_ncu_dram_traffic.json (" + rec["report"] + ")"
                     break
         roofline = {"kernel": dom, "bound": "hbm", "achieved": r["gbps"], "peak": peak, "unit": "GB/s",
-                    "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "frac": r["frac"], "traffic": traffic,
+                    "traffic_source": {"source": "static", "file": traffic_src,
+                                       "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed "
+                                       "`ncu --set full` capture of the same workload; NOT measured in this run"} if traffic else None,
                     "peak_source": peak_src, "share_of_step": r["share"],
                     "timing": "CUDA event pair per launch on the launching stream, 3 extra steps after the timed region",
                     "algorithmic_bytes_per_launch": ab[dom]}
     step_bytes = step_algorithmic_bytes(E, N, D, L)
-    cpu_val, cpu_dt, cores, sample = cpu_oracle_rate(steps=3, warmup=1, scale=0.25) if world == 1 else (None,) * 4
+    cpu_val, cpu_dt, cores, sample = cpu_oracle_rate(steps=2, warmup=1, scale=1.0) if world == 1 else (None,) * 4
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
@@ -410,6 +443,7 @@ def run_ours(args):
                           "formula": "SURVEY 8d: L*(4d(11E+67N)+32E), the fused two-pass ideal"},
         "kernels": kernels,
         "clocks": clocks,
+        "parity_check": parity,
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
@@ -430,6 +464,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the first-step loss / gradient check against "
+                    "the CPU oracle (about 15 s of host time)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (default: the step "
                     "is captured once into a CUDA graph and replayed)")
     args = ap.parse_args()

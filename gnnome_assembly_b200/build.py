@@ -16,7 +16,7 @@ SOURCES = ["gg_plan.cu", "gg_api.cu", "gg_prep.cu", "gg_subgraph.cu", "gg_decode
 LIBS = ["-lcudart"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DGG_BUILD"]
+         "-Xcompiler", "-fPIC", "-DGG_BUILD"]
 
 
 def _stale():

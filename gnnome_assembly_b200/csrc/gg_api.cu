@@ -9,14 +9,15 @@
 
 namespace gg {
 
+// per-device caches (one process may drive several GPUs: the reference's default device is 'cuda:3',
+// hyperparameters.py:25): everything cached about "the GPU" is keyed by the current device ordinal
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // one warp per node, 8 warps per CTA, grid-stride over the nodes.  The grid is exactly ONE wave: as many CTAs as
@@ -24,7 +25,8 @@ static int sm_count() {
 // grid of 8 CTAs per SM ran as 2.7 waves of 3 resident CTAs, the last one a third empty.
 template <class Kern>
 static unsigned node_grid(Kern kern, int64_t n) {
-  static int per_sm = 0;                      // one static per kernel instantiation
+  static int per_sm_dev[kMaxDevices] = {};    // one static per kernel instantiation, per device
+  int& per_sm = per_sm_dev[current_device()];
   if (per_sm == 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kNodeThreads, 0) != cudaSuccess || occ < 1) occ = 2;
@@ -147,7 +149,8 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     // d = 128: 16 consumer warps per SM instead of 24, every row crosses shared memory), so it is not the default.
     auto kern = edge_gate_fwd_bulk_kernel<D, NORM>;
     constexpr int kSmem = 6 * kBulkStageBytes;
-    static int per_sm = 0;
+    static int per_sm_dev[kMaxDevices] = {};
+    int& per_sm = per_sm_dev[current_device()];
     if (per_sm == 0) {
       GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
       int occ = 0;

@@ -40,6 +40,14 @@ void kernel_end(const char* name, cudaStream_t st);
     }                                                              \
   } while (0)
 
+// device ordinal of the calling thread, clamped: index of the per-device host caches
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 struct Plan {
   int64_t N = 0, E = 0;
   int32_t* src = nullptr;      // [E] internal (dst-sorted) order

@@ -907,7 +907,8 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx, kWRes>;
   constexpr int kSmem = smem_bytes<kStats, Epi, ATx, kWRes>();
   static_assert(kSmem <= 227 * 1024, "shared-memory layout exceeds 227 KB");
-  static bool attr_set = false;      // one static per template instantiation
+  static bool attr_set_dev[kMaxDevices] = {};      // one static per template instantiation, per device
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;

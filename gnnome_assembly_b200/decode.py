@@ -46,8 +46,6 @@ def adjacency_arrays(src, dst, num_nodes):
     {(src, dst): id} dictionary (graph_parser.py:69-72): of parallel edges only the LAST id is ever seen — scores and
     prefix lengths are read through that id (canon_eid)."""
     n, E = int(num_nodes), int(src.numel())
-    if E and bool((src == dst).any()):
-        raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
     ids = torch.arange(E, device=src.device, dtype=torch.int64)
     if E:
         _, inv = torch.unique(src * max(n, 1) + dst, return_inverse=True)
@@ -55,12 +53,17 @@ def adjacency_arrays(src, dst, num_nodes):
         canon = last[inv]
     else:
         canon = ids
+    # self loops: the reference drops them before decoding (dgl.remove_self_loop, inference.py:187).  Here they are
+    # left out of the successor / predecessor lists and get sampling weight 0 (gg_decode_edge_weights), while every
+    # other edge KEEPS its id, so scores / prefix lengths stay addressed by the caller's edge ids.
+    keep = src != dst
+    ksrc, kdst, kcanon = src[keep], dst[keep], canon[keep]
     out = []
-    for key, other in ((src, dst), (dst, src)):
+    for key, other in ((ksrc, kdst), (kdst, ksrc)):
         order = torch.argsort(key, stable=True)
         ptr_ = torch.zeros(n + 1, dtype=torch.int64, device=src.device)
         ptr_[1:] = torch.cumsum(torch.bincount(key, minlength=n), 0)
-        out += [ptr_, other[order], canon[order]]
+        out += [ptr_, other[order], kcanon[order]]
     return (*out, canon)
 
 
@@ -79,8 +82,6 @@ class DecodeGraph:
             arrays = adjacency_arrays(src_t.to(self.device), dst_t.to(self.device), self.num_nodes)
         else:
             src_np, dst_np = src_t.cpu().numpy(), dst_t.cpu().numpy()
-            if np.any(src_np == dst_np):
-                raise ValueError("decode: the graph has self loops (the reference removes them, inference.py:187)")
             s_ptr, s_node, s_eid = self._from_dict(succs, edges, forward=True)
             p_ptr, p_node, p_eid = self._from_dict(preds, edges, forward=False)
             canon = np.array([edges[(int(a), int(b))] for a, b in zip(src_np, dst_np)], dtype=np.int64)

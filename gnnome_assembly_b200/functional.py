@@ -14,8 +14,29 @@ from ._lib import check, ptr
 NORM_BATCH, NORM_LAYER = 0, 1
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+class _on:
+    """Device guard for one C-ABI call: makes the tensors' device current (kernel launches, TMA descriptors and the
+    per-device caches of the library follow the CURRENT device) and yields that device's current stream.  The
+    reference's default device is 'cuda:3' with no set_device (hyperparameters.py:25), so the current device is
+    NOT the tensors' device in general.  Every tensor of the call (and the plan) must share one device."""
+
+    def __init__(self, *tensors, plan=None):
+        devs = {t.device for t in tensors if t is not None}
+        if plan is not None:
+            devs.add(plan.device)
+        if len(devs) != 1:
+            raise RuntimeError(f"gnnome_assembly_b200: tensors / graph plan of one call live on different devices: {sorted(map(str, devs))}")
+        (self.dev,) = devs
+        if self.dev.type != "cuda":
+            raise RuntimeError("gnnome_assembly_b200: tensors must live on a CUDA device (no CPU path)")
+
+    def __enter__(self):
+        self._guard = torch.cuda.device(self.dev)
+        self._guard.__enter__()
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def __exit__(self, *exc):
+        return self._guard.__exit__(*exc)
 
 
 def _cuda_f32(*tensors):
@@ -43,7 +64,8 @@ class _PermuteRows(torch.autograd.Function):
         rows = x.shape[0]
         width = x.numel() // rows if rows else 1
         out = torch.empty_like(x)
-        check(_lib.lib().gg_gather_rows(rows, width, ptr(x), ptr(idx), ptr(out), _stream()), "gg_gather_rows")
+        with _on(x, idx) as st:
+            check(_lib.lib().gg_gather_rows(rows, width, ptr(x), ptr(idx), ptr(out), st), "gg_gather_rows")
         return out
 
     @staticmethod
@@ -52,7 +74,8 @@ class _PermuteRows(torch.autograd.Function):
         rows = g.shape[0]
         width = g.numel() // rows if rows else 1
         out = torch.empty_like(g)
-        check(_lib.lib().gg_gather_rows(rows, width, ptr(g), ptr(ctx.inv), ptr(out), _stream()), "gg_gather_rows")
+        with _on(g, ctx.inv) as st:
+            check(_lib.lib().gg_gather_rows(rows, width, ptr(g), ptr(ctx.inv), ptr(out), st), "gg_gather_rows")
         return out, None, None
 
 
@@ -68,7 +91,8 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = W.shape[0]
         y = torch.empty(M, N, device=x.device, dtype=torch.float32)
-        check(_lib.lib().gg_linear_fwd(M, N, K, ptr(x), ptr(W), ptr(b), 0, ptr(y), _stream()), "gg_linear_fwd")
+        with _on(x, W, b) as st:
+            check(_lib.lib().gg_linear_fwd(M, N, K, ptr(x), ptr(W), ptr(b), 0, ptr(y), st), "gg_linear_fwd")
         ctx.save_for_backward(x, W)
         ctx.has_bias = b is not None
         return y
@@ -81,12 +105,13 @@ class _Linear(torch.autograd.Function):
         N = W.shape[0]
         lib = _lib.lib()
         gx = None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            check(lib.gg_linear_bwd_data(M, N, K, ptr(g), ptr(W), None, None, ptr(gx), _stream()), "gg_linear_bwd_data")
         dW = torch.empty_like(W)
         db = torch.empty(N, device=W.device, dtype=torch.float32) if ctx.has_bias else None
-        check(lib.gg_linear_bwd_weight(M, N, K, ptr(g), ptr(x), ptr(dW), ptr(db), _stream()), "gg_linear_bwd_weight")
+        with _on(g, x, W) as st:
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                check(lib.gg_linear_bwd_data(M, N, K, ptr(g), ptr(W), None, None, ptr(gx), st), "gg_linear_bwd_data")
+            check(lib.gg_linear_bwd_weight(M, N, K, ptr(g), ptr(x), ptr(dW), ptr(db), st), "gg_linear_bwd_weight")
         return gx, dW, db
 
 
@@ -116,9 +141,10 @@ class _EdgeMLP(torch.autograd.Function):
         E, K = e.shape
         Hh, d = W1.shape[0], W2.shape[0]
         hid = torch.empty(E, Hh, device=e.device, dtype=torch.float32)
-        check(lib.gg_linear_fwd(E, Hh, K, ptr(e), ptr(W1), ptr(b1), 1, ptr(hid), _stream()), "gg_linear_fwd")
         out = torch.empty(E, d, device=e.device, dtype=torch.float32)
-        check(lib.gg_linear_fwd(E, d, Hh, ptr(hid), ptr(W2), ptr(b2), 0, ptr(out), _stream()), "gg_linear_fwd")
+        with _on(e, W1, b1, W2, b2) as st:
+            check(lib.gg_linear_fwd(E, Hh, K, ptr(e), ptr(W1), ptr(b1), 1, ptr(hid), st), "gg_linear_fwd")
+            check(lib.gg_linear_fwd(E, d, Hh, ptr(hid), ptr(W2), ptr(b2), 0, ptr(out), st), "gg_linear_fwd")
         ctx.save_for_backward(e, W1, W2, hid)
         return out
 
@@ -131,19 +157,18 @@ class _EdgeMLP(torch.autograd.Function):
         Hh, d = W1.shape[0], W2.shape[0]
         dW2 = torch.empty_like(W2)
         db2 = torch.empty(d, device=g.device, dtype=torch.float32)
-        if Hh == 16 and K == 4 and d in (64, 128):
-            # one pass over g: dW2, db2, the ReLU-masked hidden gradient (never stored), dW1, db1
-            dW1 = torch.empty_like(W1)
-            db1 = torch.empty(Hh, device=g.device, dtype=torch.float32)
-            check(lib.gg_edge_mlp_bwd(E, d, Hh, K, ptr(g), ptr(hid), ptr(e), ptr(W2), ptr(dW1), ptr(db1), ptr(dW2),
-                                      ptr(db2), _stream()), "gg_edge_mlp_bwd")
-            return None, dW1, db1, dW2, db2
-        check(lib.gg_linear_bwd_weight(E, d, Hh, ptr(g), ptr(hid), ptr(dW2), ptr(db2), _stream()), "gg_linear_bwd_weight")
-        g_hid = torch.empty_like(hid)
-        check(lib.gg_linear_bwd_data(E, d, Hh, ptr(g), ptr(W2), None, ptr(hid), ptr(g_hid), _stream()), "gg_linear_bwd_data")
         dW1 = torch.empty_like(W1)
         db1 = torch.empty(Hh, device=g.device, dtype=torch.float32)
-        check(lib.gg_linear_bwd_weight(E, Hh, K, ptr(g_hid), ptr(e), ptr(dW1), ptr(db1), _stream()), "gg_linear_bwd_weight")
+        with _on(g, e, W1, W2, hid) as st:
+            if Hh == 16 and K == 4 and d in (64, 128):
+                # one pass over g: dW2, db2, the ReLU-masked hidden gradient (never stored), dW1, db1
+                check(lib.gg_edge_mlp_bwd(E, d, Hh, K, ptr(g), ptr(hid), ptr(e), ptr(W2), ptr(dW1), ptr(db1), ptr(dW2),
+                                          ptr(db2), st), "gg_edge_mlp_bwd")
+                return None, dW1, db1, dW2, db2
+            check(lib.gg_linear_bwd_weight(E, d, Hh, ptr(g), ptr(hid), ptr(dW2), ptr(db2), st), "gg_linear_bwd_weight")
+            g_hid = torch.empty_like(hid)
+            check(lib.gg_linear_bwd_data(E, d, Hh, ptr(g), ptr(W2), None, ptr(hid), ptr(g_hid), st), "gg_linear_bwd_data")
+            check(lib.gg_linear_bwd_weight(E, Hh, K, ptr(g_hid), ptr(e), ptr(dW1), ptr(db1), st), "gg_linear_bwd_weight")
         return None, dW1, db1, dW2, db2
 
 
@@ -170,9 +195,10 @@ class _GatedGCNLayer(torch.autograd.Function):
         P, t, z = torch.empty(N, 5 * d, **f32), torch.empty(E, d, **f32), torch.empty(N, d, **f32)
         agg = torch.empty(5, N, d, **f32)
         stats = torch.empty(4 * d, device=dev, dtype=torch.float64)
-        check(_lib.lib().gg_layer_fwd(plan.handle, d, norm_kind, int(residual), ptr(h), ptr(e), ptr(Wn), ptr(bn),
-                                      ptr(B3), ptr(b3), ptr(ge), ptr(be), ptr(gh), ptr(bh), ptr(h_out), ptr(e_out),
-                                      ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), _stream()), "gg_layer_fwd")
+        with _on(h, e, Wn, bn, B3, b3, ge, be, gh, bh, plan=plan) as st:
+            check(_lib.lib().gg_layer_fwd(plan.handle, d, norm_kind, int(residual), ptr(h), ptr(e), ptr(Wn), ptr(bn),
+                                          ptr(B3), ptr(b3), ptr(ge), ptr(be), ptr(gh), ptr(bh), ptr(h_out), ptr(e_out),
+                                          ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), st), "gg_layer_fwd")
         ctx.plan, ctx.norm_kind, ctx.residual = plan, norm_kind, int(residual)
         ctx.save_for_backward(h, e, e_out, Wn, B3, ge, be, gh, bh, P, t, z, agg, stats)
         return h_out, e_out
@@ -194,11 +220,12 @@ class _GatedGCNLayer(torch.autograd.Function):
         dB3, db3 = torch.empty(d, d, **f32), torch.empty(d, **f32)
         dge, dbe, dgh, dbh = (torch.empty(d, **f32) for _ in range(4))
         bstats = torch.empty(4 * d, device=dev, dtype=torch.float64)
-        check(_lib.lib().gg_layer_bwd(
-            plan.handle, d, ctx.norm_kind, ctx.residual, ptr(h), ptr(e), ptr(e_out), ptr(Wn), ptr(B3), ptr(ge),
-            ptr(be), ptr(gh), ptr(bh), ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), ptr(g_h), ptr(g_e),
-            ptr(g_h_in), ptr(g_e_in), ptr(dWn), ptr(dbn), ptr(dB3), ptr(db3), ptr(dge), ptr(dbe), ptr(dgh), ptr(dbh),
-            ptr(gP), ptr(G), ptr(g_eo), ptr(g_t), ptr(bstats), _stream()), "gg_layer_bwd")
+        with _on(h, e, g_h, g_e, plan=plan) as st:
+            check(_lib.lib().gg_layer_bwd(
+                plan.handle, d, ctx.norm_kind, ctx.residual, ptr(h), ptr(e), ptr(e_out), ptr(Wn), ptr(B3), ptr(ge),
+                ptr(be), ptr(gh), ptr(bh), ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), ptr(g_h), ptr(g_e),
+                ptr(g_h_in), ptr(g_e_in), ptr(dWn), ptr(dbn), ptr(dB3), ptr(db3), ptr(dge), ptr(dbe), ptr(dgh), ptr(dbh),
+                ptr(gP), ptr(G), ptr(g_eo), ptr(g_t), ptr(bstats), st), "gg_layer_bwd")
         return None, None, None, g_h_in, g_e_in, dWn, dbn, dB3, db3, dge, dbe, dgh, dbh
 
 
@@ -221,8 +248,9 @@ class _Score(torch.autograd.Function):
         score, Q = torch.empty(E, **f32), torch.empty(N, 2 * H, **f32)
         need_grad = any(ctx.needs_input_grad)
         hid = torch.empty(E, H, **f32) if need_grad else None
-        check(_lib.lib().gg_score_fwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(bq), ptr(W1e), ptr(w2), ptr(b2),
-                                      ptr(score), ptr(Q), ptr(hid), _stream()), "gg_score_fwd")
+        with _on(x, e, Wq, bq, W1e, w2, b2, plan=plan) as st:
+            check(_lib.lib().gg_score_fwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(bq), ptr(W1e), ptr(w2), ptr(b2),
+                                          ptr(score), ptr(Q), ptr(hid), st), "gg_score_fwd")
         ctx.plan = plan
         if need_grad:
             ctx.save_for_backward(x, e, Wq, W1e, w2, hid)
@@ -244,9 +272,10 @@ class _Score(torch.autograd.Function):
         gQ = torch.empty(N, 2 * H, **f32)
         red = torch.empty(2 * H + 1, device=dev, dtype=torch.float64)
         gpre = torch.empty_like(hid)
-        check(_lib.lib().gg_score_bwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(W1e), ptr(w2), ptr(g), ptr(hid),
-                                      ptr(g_x), ptr(g_e), ptr(dWq), ptr(dbq), ptr(dW1e), ptr(dw2), ptr(db2), ptr(gpre),
-                                      ptr(gQ), ptr(red), _stream()), "gg_score_bwd")
+        with _on(x, e, g, hid, plan=plan) as st:
+            check(_lib.lib().gg_score_bwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(W1e), ptr(w2), ptr(g), ptr(hid),
+                                          ptr(g_x), ptr(g_e), ptr(dWq), ptr(dbq), ptr(dW1e), ptr(dw2), ptr(db2), ptr(gpre),
+                                          ptr(gQ), ptr(red), st), "gg_score_bwd")
         return None, g_x, g_e, dWq, dbq, dW1e, dw2, db2
 
 

@@ -30,6 +30,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr
+from .functional import _on
 from .graph import AssemblyGraph
 from .plan import _PLAN_CACHE, plan_for
 
@@ -45,8 +46,8 @@ def _gather(t, idx32, idx64):
         width = t.numel() // t.shape[0]
         out = torch.empty((rows,) + tuple(t.shape[1:]), device=t.device, dtype=torch.float32)
         if rows:
-            check(_lib.lib().gg_gather_rows(rows, width, ptr(t), ptr(idx32), ptr(out),
-                                            torch.cuda.current_stream().cuda_stream), "gg_gather_rows")
+            with _on(t, idx32) as st:
+                check(_lib.lib().gg_gather_rows(rows, width, ptr(t), ptr(idx32), ptr(out), st), "gg_gather_rows")
         return out
     return t[idx64]
 

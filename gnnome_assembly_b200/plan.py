@@ -145,7 +145,45 @@ class GraphPlan:
         return self.array("dst")
 
 
-_PLAN_CACHE = weakref.WeakKeyDictionary()
+_PLAN_CACHE = weakref.WeakKeyDictionary()      # graph object -> plan (fast path: the same object comes back)
+
+# The reference loop does `g = g.to(device)` every step (train.py:243, :394; inference.py:326): for a CPU-resident
+# dataset graph DGL returns a NEW graph object each time, so an identity-keyed cache alone would rebuild the plan on
+# every step.  Second level: a small LRU keyed by a structural fingerprint of the edge list (N, E, device and two
+# order-sensitive 64-bit hashes computed where the edge list lives; one 16-byte D2H), so a graph with the same
+# structure finds its plan whatever object carries it.
+_CONTENT_CACHE = {}                              # fingerprint -> plan, insertion-ordered (LRU)
+_CONTENT_CACHE_MAX_EDGES = 256 << 20             # bound on the summed edge count of the plans kept alive
+PLAN_STATS = {"built": 0, "hit_object": 0, "hit_content": 0}
+
+
+def _fingerprint(src, dst, num_nodes, device):
+    E = int(src.numel())
+    if E == 0:
+        return (int(num_nodes), 0, str(device), 0, 0)
+    s, d = src.reshape(-1).to(torch.int64), dst.reshape(-1).to(torch.int64)
+    pos = torch.arange(1, E + 1, device=s.device, dtype=torch.int64)
+    # int64 arithmetic wraps: order-sensitive multiplicative hashes (the internal order depends on the edge order)
+    h1 = ((s * -7046029254386353131 + d * -4417276706812531889) * pos).sum()
+    h2 = ((s ^ (d * 1099511628211)) * (pos * 2654435761 + 97)).sum()
+    h = torch.stack((h1, h2)).tolist()
+    return (int(num_nodes), E, str(device), int(h[0]), int(h[1]))
+
+
+def _content_cache_put(key, plan):
+    _CONTENT_CACHE.pop(key, None)
+    _CONTENT_CACHE[key] = plan
+    total = sum(p.num_edges for p in _CONTENT_CACHE.values())
+    while total > _CONTENT_CACHE_MAX_EDGES and len(_CONTENT_CACHE) > 1:
+        _, old = next(iter(_CONTENT_CACHE.items()))
+        total -= old.num_edges
+        _CONTENT_CACHE.pop(next(iter(_CONTENT_CACHE)))
+
+
+def clear_plan_cache():
+    _CONTENT_CACHE.clear()
+    for k in list(_PLAN_CACHE.keys()):
+        _PLAN_CACHE.pop(k, None)
 
 
 def plan_for(graph, device=None):
@@ -162,12 +200,36 @@ def plan_for(graph, device=None):
         plan = _PLAN_CACHE.get(graph)
     except TypeError:
         plan = None
-    if plan is not None and (device is None or plan.device == torch.device(device)):
+    origin = getattr(graph, "_origin", None)      # AssemblyGraph.to() / .int() / .long(): same structure, new object
+    if plan is None and origin is not None:
+        plan = _PLAN_CACHE.get(origin)
+    if plan is not None and (device is None or plan.device == _resolve(device)):
+        PLAN_STATS["hit_object"] += 1
         return plan
     src, dst = graph.edges()
-    plan = GraphPlan(src, dst, graph.num_nodes(), device)
-    try:
-        _PLAN_CACHE[graph] = plan
-    except TypeError:
-        pass
+    src, dst = torch.as_tensor(src), torch.as_tensor(dst)
+    if device is None:
+        device = src.device if src.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    device = _resolve(device)
+    key = _fingerprint(src, dst, graph.num_nodes(), device)
+    plan = _CONTENT_CACHE.get(key)
+    if plan is None:
+        plan = GraphPlan(src, dst, graph.num_nodes(), device)
+        PLAN_STATS["built"] += 1
+    else:
+        PLAN_STATS["hit_content"] += 1
+    _content_cache_put(key, plan)
+    for key_obj in (graph, origin):
+        if key_obj is not None:
+            try:
+                _PLAN_CACHE[key_obj] = plan
+            except TypeError:
+                pass
     return plan
+
+
+def _resolve(device):
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device

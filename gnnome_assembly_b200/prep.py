@@ -11,11 +11,8 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr
+from .functional import _on
 from .plan import plan_for
-
-
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
 
 
 def preprocess_features(overlap_length, overlap_similarity):
@@ -27,7 +24,8 @@ def preprocess_features(overlap_length, overlap_similarity):
     E = a.numel()
     out = torch.empty(E, 2, device=a.device, dtype=torch.float32)
     ws = torch.empty(4, device=a.device, dtype=torch.float64)
-    check(_lib.lib().gg_prep_edge_features(E, ptr(a), ptr(b), ptr(out), ptr(ws), _stream()), "gg_prep_edge_features")
+    with _on(a, b) as st:
+        check(_lib.lib().gg_prep_edge_features(E, ptr(a), ptr(b), ptr(out), ptr(ws), st), "gg_prep_edge_features")
     return out
 
 
@@ -37,8 +35,8 @@ def positional_encoding(graph, pe_dim=16, alpha=0.95, device=None):
     N = plan.num_nodes
     out = torch.empty(N, 2 + pe_dim, device=plan.device, dtype=torch.float32)
     ws = torch.empty(3 * max(N, 1), device=plan.device, dtype=torch.float64)
-    with torch.cuda.device(plan.device):
-        check(_lib.lib().gg_prep_pe(plan.handle, pe_dim, float(alpha), ptr(out), ptr(ws), _stream()), "gg_prep_pe")
+    with _on(out, plan=plan) as st:
+        check(_lib.lib().gg_prep_pe(plan.handle, pe_dim, float(alpha), ptr(out), ptr(ws), st), "gg_prep_pe")
     return out
 
 
@@ -51,7 +49,8 @@ class _BceMetrics(torch.autograd.Function):
             raise RuntimeError("gnnome_assembly_b200.prep: CUDA tensors expected (no CPU path)")
         E = s.numel()
         out = torch.empty(5, device=s.device, dtype=torch.float64)
-        check(_lib.lib().gg_bce_metrics_fwd(E, ptr(s), ptr(t), float(pos_weight), ptr(out), _stream()), "gg_bce_metrics_fwd")
+        with _on(s, t) as st:
+            check(_lib.lib().gg_bce_metrics_fwd(E, ptr(s), ptr(t), float(pos_weight), ptr(out), st), "gg_bce_metrics_fwd")
         ctx.save_for_backward(s, t)
         ctx.pos_weight, ctx.shape = float(pos_weight), scores.shape
         loss = (out[0] / max(E, 1)).to(torch.float32)
@@ -64,7 +63,8 @@ class _BceMetrics(torch.autograd.Function):
         s, t = ctx.saved_tensors
         g = torch.empty_like(s)
         gl = g_loss.reshape(1).to(torch.float32).contiguous()
-        check(_lib.lib().gg_bce_bwd(s.numel(), ptr(s), ptr(t), ctx.pos_weight, ptr(gl), ptr(g), _stream()), "gg_bce_bwd")
+        with _on(s, t, gl) as st:
+            check(_lib.lib().gg_bce_bwd(s.numel(), ptr(s), ptr(t), ctx.pos_weight, ptr(gl), ptr(g), st), "gg_bce_bwd")
         return g.reshape(ctx.shape), None, None
 
 

@@ -52,8 +52,11 @@ def test_adjacency_arrays_match_reference_dictionaries(n, m):
         assert se[sp[u]:sp[u + 1]].tolist() == [eid[(u, v)] for v in succs[u]]
         assert pe[pp[u]:pp[u + 1]].tolist() == [eid[(v, u)] for v in preds[u]]
     assert canon.tolist() == [eid[(a, b)] for a, b in zip(src.tolist(), dst.tolist())]
-    with pytest.raises(ValueError, match="self loops"):
-        adjacency_arrays(torch.tensor([0, 1]), torch.tensor([1, 1]), 2)
+    # self loops are dropped from the lists (dgl.remove_self_loop, inference.py:187) but every other edge keeps its id
+    sp, sn, se, pp, pn, pe, canon = [a.numpy() for a in adjacency_arrays(torch.tensor([0, 1, 1]), torch.tensor([1, 1, 0]), 2)]
+    assert sp.tolist() == [0, 1, 2] and sn.tolist() == [1, 0] and se.tolist() == [0, 2]
+    assert pp.tolist() == [0, 1, 2] and pn.tolist() == [1, 0] and pe.tolist() == [2, 0]
+    assert canon.tolist() == [0, 1, 2]
 
 
 def test_oracle_walk_semantics_small():
@@ -210,8 +213,16 @@ def test_gpu_decode_full_size_properties():
 
 
 @pytest.mark.gpu
-def test_gpu_decode_rejects_self_loops_and_cpu_only_box():
+def test_gpu_decode_drops_self_loops():
+    """A self loop never enters a walk and is never sampled (inference.py:187); the other edges keep their ids."""
     _dev()
-    from gnnome_assembly_b200.decode import DecodeGraph
-    with pytest.raises(ValueError, match="self loops"):
-        DecodeGraph(np.array([0, 1]), np.array([1, 1]), 2, "cuda:0")
+    from gnnome_assembly_b200 import decode
+    dg = decode.DecodeGraph(np.array([0, 1, 1]), np.array([1, 1, 0]), 2, "cuda:0")
+    assert dg.succ_node.tolist() == [1, 0] and dg.succ_eid.tolist() == [0, 2]
+    vis = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    w = torch.empty(3, device="cuda:0")
+    sc = torch.zeros(3, device="cuda:0")
+    from gnnome_assembly_b200 import _lib
+    _lib.check(_lib.lib().gg_decode_edge_weights(3, dg.src.data_ptr(), dg.dst.data_ptr(), sc.data_ptr(), vis.data_ptr(),
+                                                 w.data_ptr(), torch.cuda.current_stream().cuda_stream), "w")
+    assert w.tolist() == [0.5, 0.0, 0.5]

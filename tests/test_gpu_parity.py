@@ -232,7 +232,7 @@ def test_edge_gate_bulk_staged_kernel_is_bit_identical(d, batch_norm):
     assert torch.equal(e0, e1) and torch.equal(h0, h1)
 
 
-@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("d", [64, 128, 256])
 def test_score_predictor_matches_oracle(d):
     dev = _dev()
     O = _oracle()

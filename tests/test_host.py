@@ -163,3 +163,87 @@ def test_grad_bucket_allreduce_gloo_world2():
     for _, a, b in res:
         assert torch.allclose(a, torch.full((3, 4), 3.0))
         assert torch.allclose(b, torch.full((3, 4), 2.0))
+
+
+# ------------------------------------------------------------------------------------------ graph files, dgl stand-in
+def test_graph_file_round_trip(tmp_path):
+    """DGL-free graph container (graph_io.py) behind dgl.save_graphs / dgl.load_graphs (graph_dataset.py:72,129)."""
+    from gnnome_assembly_b200.graph import AssemblyGraph
+    from gnnome_assembly_b200.graph_io import load_graphs, save_graphs
+    rng = np.random.default_rng(0)
+    graphs = []
+    for n, m, idt in ((5, 0, torch.int64), (40, 300, torch.int32), (1000, 7000, torch.int64)):
+        g = AssemblyGraph(torch.from_numpy(rng.integers(0, n, m)).to(idt), torch.from_numpy(rng.integers(0, n, m)).to(idt), n)
+        g.ndata["read_length"] = torch.from_numpy(rng.integers(1000, 30000, n))
+        g.ndata["pe"] = torch.randn(n, 3)
+        g.edata["overlap_similarity"] = torch.rand(m)
+        g.edata["y"] = (torch.rand(m) > 0.5).float()
+        graphs.append(g)
+    p = str(tmp_path / "7.dgl")
+    save_graphs(p, graphs, {"glabel": torch.arange(3)})
+    back, labels = load_graphs(p)
+    assert torch.equal(labels["glabel"], torch.arange(3)) and len(back) == 3
+    for a, b in zip(graphs, back):
+        assert a.num_nodes() == b.num_nodes() and a.edges()[0].dtype == b.edges()[0].dtype
+        assert torch.equal(a.edges()[0], b.edges()[0]) and torch.equal(a.edges()[1], b.edges()[1])
+        for k in a.ndata:
+            assert torch.equal(a.ndata[k], b.ndata[k]) and a.ndata[k].dtype == b.ndata[k].dtype
+        for k in a.edata:
+            assert torch.equal(a.edata[k], b.edata[k])
+    (only,), _ = load_graphs(p, idx_list=[1])
+    assert only.num_nodes() == 40
+    with open(str(tmp_path / "bad.dgl"), "wb") as f:
+        f.write(b"\x00" * 64)
+    with pytest.raises(ValueError, match="not a gnnome_assembly_b200 graph file"):
+        load_graphs(str(tmp_path / "bad.dgl"))
+
+
+def test_dgl_standin_surface():
+    """dropin/dgl covers the names the reference's loops touch (train.py:17-18,172,292-293; utils.py:34,68,102-124;
+    graph_dataset.py:5,72,129; inference.py:184,271-273) and follows DGL's sub-graph conventions."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "dgl_standin", os.path.join(ROOT, "gnnome_assembly_b200", "dropin", "dgl", "__init__.py"),
+        submodule_search_locations=[os.path.join(ROOT, "gnnome_assembly_b200", "dropin", "dgl")])
+    dgl = importlib.util.module_from_spec(spec)
+    sys.modules["dgl_standin"] = dgl
+    spec.loader.exec_module(dgl)
+    for name in ("graph", "seed", "load_graphs", "save_graphs", "remove_self_loop", "node_subgraph", "reverse", "NID", "EID"):
+        assert hasattr(dgl, name), name
+    for name in ("ClusterGCNSampler", "DataLoader", "MultiLayerFullNeighborSampler", "GraphDataLoader"):
+        assert hasattr(dgl.dataloading, name), name
+    assert hasattr(dgl.data, "DGLDataset")
+    g = dgl.graph((torch.tensor([0, 1, 2, 2, 3]), torch.tensor([1, 2, 0, 2, 1])), num_nodes=5)
+    g.edata["w"] = torch.arange(5.0)
+    g.ndata["h"] = torch.arange(5.0)
+    assert g.int().edges()[0].dtype == torch.int32 and g.int().long().edges()[0].dtype == torch.int64
+    assert g.in_degrees().tolist() == [1, 2, 2, 0, 0] and g.out_degrees().tolist() == [1, 1, 2, 1, 0]
+    A = g.adjacency_matrix(scipy_fmt="csr")
+    assert A.shape == (5, 5) and A[2, 2] == 1 and A[3, 1] == 1 and A.sum() == 5
+    r = dgl.remove_self_loop(g)
+    assert r.num_edges() == 4 and r.edata["w"].tolist() == [0.0, 1.0, 2.0, 4.0]
+    s = dgl.node_subgraph(g, torch.tensor([2, 0, 1]))
+    assert s.ndata[dgl.NID].tolist() == [2, 0, 1] and s.edata[dgl.EID].tolist() == [0, 1, 2, 3]
+    assert s.edges()[0].tolist() == [1, 2, 0, 0] and s.edges()[1].tolist() == [2, 0, 1, 0]
+    assert s.ndata["h"].tolist() == [2.0, 0.0, 1.0]
+    rv = dgl.reverse(g, copy_edata=True)
+    assert rv.edges()[0].tolist() == g.edges()[1].tolist() and rv.edata["w"].tolist() == g.edata["w"].tolist()
+    # moving / casting keeps the structure: the derived graph points at its origin, whose GraphPlan it will share
+    assert g.int()._origin is g and g.int().long()._origin is g
+
+
+def test_plan_fingerprint_is_structural():
+    """plan.py: the second-level plan cache is keyed by the edge list's content, so `g.to(device)` returning a new
+    object every step (train.py:243) does not rebuild the plan."""
+    from gnnome_assembly_b200.plan import _fingerprint
+    rng = np.random.default_rng(1)
+    s, d = torch.from_numpy(rng.integers(0, 50, 400)), torch.from_numpy(rng.integers(0, 50, 400))
+    k = _fingerprint(s, d, 50, "cuda:0")
+    assert k == _fingerprint(s.clone().int(), d.clone().int(), 50, "cuda:0")
+    perm = torch.from_numpy(rng.permutation(400))
+    assert k != _fingerprint(s[perm], d[perm], 50, "cuda:0")           # the internal order depends on the edge order
+    assert k != _fingerprint(d, s, 50, "cuda:0") and k != _fingerprint(s, d, 51, "cuda:0")
+    assert k != _fingerprint(s, d, 50, "cuda:1")
+    s2 = s.clone()
+    s2[17] = (s2[17] + 1) % 50
+    assert k != _fingerprint(s2, d, 50, "cuda:0")
