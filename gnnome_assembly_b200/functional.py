@@ -31,12 +31,16 @@ class _on:
             raise RuntimeError("gnnome_assembly_b200: tensors must live on a CUDA device (no CPU path)")
 
     def __enter__(self):
-        self._guard = torch.cuda.device(self.dev)
-        self._guard.__enter__()
+        self._guard = None
+        if torch.cuda.current_device() != self.dev.index:          # the common case needs no switch at all
+            self._guard = torch.cuda.device(self.dev)
+            self._guard.__enter__()
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def __exit__(self, *exc):
-        return self._guard.__exit__(*exc)
+        if self._guard is not None:
+            return self._guard.__exit__(*exc)
+        return False
 
 
 def _cuda_f32(*tensors):

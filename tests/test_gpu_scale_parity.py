@@ -120,10 +120,17 @@ def test_layer_gradients_100k_edges_vs_fp64(d):
     gr = {k: p.grad for k, p in ours.named_parameters()}
     gr64 = {k: p.grad for k, p in ref.named_parameters()}
     gr["__h"], gr["__e"], gr64["__h"], gr64["__e"] = hd.grad, ed.grad, h64.grad, e64.grad
-    # 100 k x d pre-ReLU values: a handful sit within fp32 rounding of 0 and may flip their mask; one flip moves a
-    # weight gradient by one edge's share of a 100 k-edge sum, far inside rtol
-    bad = O.grads_close(gr, gr64, rtol=1e-3, atol_frac=1e-5)
+    # 100 k x d pre-ReLU values with unit-variance inputs: ~10 of them sit within fp32 rounding of 0 and flip their ReLU
+    # mask against the fp64 oracle; each flip moves one row of dB3 (and one entry of the node sums) by |g_eo e_in| = O(1..10),
+    # i.e. a few 1e-3 of the largest entry.  The max-norm bound therefore is 1e-2, and the discriminating check is the
+    # Frobenius one: sparse flips stay below 1e-3 of the tensor's norm, whereas ONE wrong / missing 128-row tile out of
+    # 780 (a broken phase flip or accumulator swap) would show up as ~3e-2.
+    bad = O.grads_close(gr, gr64, rtol=1e-2, atol_frac=1e-5)
     assert bad == [], bad[:4]
+    scale = max(float(v.norm()) for v in gr64.values())
+    for k, r in gr64.items():
+        err = float((gr[k].detach().double().cpu() - r).norm())
+        assert err <= 2e-3 * float(r.norm()) + 1e-6 * scale, (k, err, float(r.norm()))
 
 
 def test_config5_point_1m_edges_d256():
