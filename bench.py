@@ -280,21 +280,24 @@ def run_ours(args):
         oracle = OracleModel(1, 2, D, HID_E, L, HID_S, True, NB_PE)
         oracle.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
         torch.set_num_threads(os.cpu_count() or 1)
-        loss0 = bce_loss(model(graph, None, d_e, d_pe), d_y)
-        opt.zero_grad(set_to_none=True)
+        # a twin of the model (same class, same weights): a backward on the default stream would tie the timed model's
+        # AccumulateGrad nodes to that stream and invalidate the CUDA-graph capture of the step later on
+        import copy
+        twin = copy.deepcopy(model)
+        loss0 = bce_loss(twin(graph, None, d_e, d_pe), d_y)
         loss0.backward()
         src64, dst64 = torch.from_numpy(g.src.astype(np.int64)), torch.from_numpy(g.dst.astype(np.int64))
         ref0 = oracle_bce(oracle(src64, dst64, N, torch.from_numpy(g.e), torch.from_numpy(g.pe)), torch.from_numpy(g.y), POS_WEIGHT)
         ref0.backward()
-        bad = grads_close({k: p.grad for k, p in model.named_parameters()},
+        bad = grads_close({k: p.grad for k, p in twin.named_parameters()},
                           {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5)
-        parity = {"first_step_loss": float(loss0), "oracle_loss": float(ref0), "abs_diff": abs(float(loss0) - float(ref0)),
+        parity = {"first_step_loss": float(loss0.detach()), "oracle_loss": float(ref0.detach()), "abs_diff": abs(float(loss0.detach()) - float(ref0.detach())),
                   "grad_tensors_checked": len(list(oracle.parameters())), "grad_mismatches": len(bad),
                   "tolerance": "loss 1e-5 relative; gradients rtol 2e-3 of each tensor's max + 1e-5 of the model's max"}
         assert parity["abs_diff"] < 1e-5 * max(1.0, abs(float(ref0))), f"bench: first-step loss differs from the oracle: {parity}"
         assert not bad, f"bench: gradients differ from the oracle: {bad[:3]}"
-        opt.zero_grad(set_to_none=True)
-        del oracle
+        del oracle, twin, loss0
+        torch.cuda.synchronize()
 
     graphed = None
     launches_per_step = None

@@ -125,7 +125,10 @@ def test_layer_gradients_100k_edges_vs_fp64(d):
     # i.e. a few 1e-3 of the largest entry.  The max-norm bound therefore is 1e-2, and the discriminating check is the
     # Frobenius one: sparse flips stay below 1e-3 of the tensor's norm, whereas ONE wrong / missing 128-row tile out of
     # 780 (a broken phase flip or accumulator swap) would show up as ~3e-2.
-    bad = O.grads_close(gr, gr64, rtol=1e-2, atol_frac=1e-5)
+    # (a flipped element moves its own row of the INPUT gradient __e by |g_eo gamma rstd B3| = O(0.1), comparable to that
+    # tensor's largest entry: the input gradients are judged by the Frobenius criterion only)
+    params = [k for k in gr64 if not k.startswith("__")]
+    bad = O.grads_close({k: gr[k] for k in params}, {k: gr64[k] for k in params}, rtol=1e-2, atol_frac=1e-5)
     assert bad == [], bad[:4]
     scale = max(float(v.norm()) for v in gr64.values())
     for k, r in gr64.items():
