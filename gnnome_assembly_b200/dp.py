@@ -52,3 +52,109 @@ class GradBucket:
             p.grad = flat[off:off + n].view_as(p)
             off += n
         return flat[:self.n]
+
+
+class ArenaSync:
+    """Gradient all-reduce on the model's per-pass GradArena (flat.py), overlapped with the backward.
+
+    The backward kernels write every parameter gradient into one flat arena in flat-parameter order, so nothing has to
+    be packed.  The arena is reduced in SEGMENTS — one per GatedGCN layer, in the order the backward finishes them
+    (last layer first), then the `head` segment (encoders + predictor) — each on a side stream as soon as its layer's
+    backward has been enqueued, so the NCCL calls of layer l hide under the backward of layers l-1 ... 0.  Every rank
+    issues the same sequence of collectives; a rank without a graph in a short wave (`idle_step`) contributes zeros.
+    The sum is scaled by 1 / n_active on the side stream right after each segment's all-reduce.
+
+    Usage (one process per GPU):
+        sync = ArenaSync(model)
+        loss = criterion(model(g, x, e, pe).squeeze(-1), y); optimizer.zero_grad(); loss.backward()
+        sync.finish()                     # remaining segment + join the side stream; p.grad now holds the mean
+        optimizer.step()
+    zero_grad must leave the gradients unset (set_to_none=True, the torch >= 2.0 default): autograd then adopts the
+    arena views as .grad without a copy.  All of it can be captured into a CUDA graph (train_step.GraphedTrainStep).
+    """
+
+    def __init__(self, model, group=None, overlap=True):
+        self.model, self.group, self.overlap = model, group, overlap
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.n_active = self.world
+        self._arena, self._pending, self._comm = None, [], None
+        model.arena_hook = self._attach
+
+    # ---- plumbing
+    def _attach(self, arena):
+        self._arena = arena
+        self._pending = [name for name, _, _ in arena.layout.segments]
+        arena.on_segment_ready = self._segment_ready
+
+    def _side_stream(self, dev):
+        if dev.type != "cuda" or not self.overlap:
+            return None
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+        return self._comm
+
+    def _reduce(self, buf):
+        if self.world > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        if self.n_active != 1:
+            buf.mul_(1.0 / float(self.n_active))
+
+    def _segment(self, off, size, name):
+        arena = self._arena
+        buf = arena.tensor()[off:off + size]
+        comm = self._side_stream(buf.device)
+        if comm is None:
+            self._reduce(buf)
+        else:
+            comm.wait_stream(torch.cuda.current_stream(buf.device))
+            with torch.cuda.stream(comm):
+                self._reduce(buf)
+        if name in self._pending:
+            self._pending.remove(name)
+
+    def _segment_ready(self, off, size):
+        for name, o, s in self._arena.layout.segments:
+            if o == off and s == size:
+                self._segment(off, size, name)
+
+    # ---- API
+    def begin(self, n_active=None):
+        """Number of ranks that hold a graph in this wave (default: all)."""
+        self.n_active = self.world if n_active is None else int(n_active)
+
+    def finish(self):
+        """Reduce what the backward hooks have not reduced yet (the head segment; everything if a layer did not take
+        part in the pass), join the side stream, and make sure every .grad IS its arena slot."""
+        arena = self._arena
+        if arena is None:
+            raise RuntimeError("ArenaSync.finish: no forward pass has been run through the model")
+        seg = {name: (off, size) for name, off, size in arena.layout.segments}
+        order = [n for n in reversed(list(seg)) if n != "head"] + [n for n in seg if n == "head"]
+        for name in [n for n in order if n in self._pending]:                    # conv L-1 ... conv 0, head last
+            self._segment(*seg[name], name)
+        buf = arena.tensor()
+        comm = self._side_stream(buf.device)
+        if comm is not None:
+            torch.cuda.current_stream(buf.device).wait_stream(comm)
+        base = buf.data_ptr()
+        for p, off in arena.layout.entries:
+            if not p.requires_grad:
+                continue
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                if p.grad is not None and p.grad.data_ptr() != base + 4 * off:
+                    raise RuntimeError("ArenaSync: a gradient does not live in the pass's arena — call "
+                                       "optimizer.zero_grad(set_to_none=True) before backward")
+                p.grad = buf[off:off + p.numel()].view_as(p)
+        return buf
+
+    def idle_step(self):
+        """A rank with no graph in this wave: zero gradients through the same sequence of collectives."""
+        from .flat import GradArena, ensure_flat
+        layout = ensure_flat(self.model)
+        dev = next(self.model.parameters()).device
+        arena = GradArena(layout, dev)
+        arena.tensor().zero_()
+        self._attach(arena)
+        for p in self.model.parameters():
+            p.grad = None
+        return self.finish()

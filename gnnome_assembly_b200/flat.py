@@ -56,6 +56,7 @@ class FlatLayout:
         add([p for p in module.parameters() if id(p) not in conv_params], "head")     # encoders + predictor
         for i, c in enumerate(convs):
             add(_layer_param_order(c), f"conv{i}")
+            c.__dict__["_gg_segment"] = f"conv{i}"                    # the arena segment this layer's backward completes
         self.entries = ordered
         self.total = off
         self.offset_of = {id(p): o for p, o in ordered}
@@ -99,6 +100,7 @@ def ensure_flat(module):
         layout, flat = state
         base = flat.data_ptr()
         if (flat.device == dev and len(layout.entries) == len(params) and
+                all(id(p) in layout.offset_of for p in params) and           # (a deep copy carries stale ids)
                 all(p.data_ptr() == base + 4 * off and p.device == dev for p, off in layout.entries)):
             return layout
     if dtype != torch.float32 or any(p.dtype != torch.float32 or p.device != dev for p in params):

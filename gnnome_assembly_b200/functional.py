@@ -87,106 +87,136 @@ def permute_rows(x, idx, inv):
     return _PermuteRows.apply(x, idx, inv)
 
 
+# ----------------------------------------------------------------------------------- gradient outputs
+def _grad_out(arena, param, shape, device):
+    """Where a parameter gradient is written: its slot of the pass's GradArena (flat.py) or a fresh tensor."""
+    if arena is not None and param is not None and id(param) in arena.layout.offset_of:
+        return arena.slot(param).view(shape)
+    return torch.empty(shape, device=device, dtype=torch.float32)
+
+
+def _pad_cols(t, K4):
+    """zero-pad the last dimension to K4 columns (the kernels want K % 4 == 0: 18 -> 20, 2 -> 4)"""
+    return t if t.shape[1] == K4 else F.pad(t, (0, K4 - t.shape[1]))
+
+
 # ----------------------------------------------------------------------------------- dense linear
 class _Linear(torch.autograd.Function):
+    """nn.Linear; W may have K % 4 != 0 (padding happens here, outside autograd)."""
+
     @staticmethod
-    def forward(ctx, x, W, b):
+    def forward(ctx, x, W, b, arena, Wp, bp):
+        # Wp / bp: the nn.Parameters behind W / b (identify the arena slots); W, b are what autograd tracks
         x, W, b = _cuda_f32(x, W, b)
         M, K = x.shape
         N = W.shape[0]
+        K4 = (K + 3) & ~3
+        x4, W4 = _pad_cols(x, K4), _pad_cols(W, K4)
         y = torch.empty(M, N, device=x.device, dtype=torch.float32)
-        with _on(x, W, b) as st:
-            check(_lib.lib().gg_linear_fwd(M, N, K, ptr(x), ptr(W), ptr(b), 0, ptr(y), st), "gg_linear_fwd")
-        ctx.save_for_backward(x, W)
-        ctx.has_bias = b is not None
+        with _on(x4, W4, b) as st:
+            check(_lib.lib().gg_linear_fwd(M, N, K4, ptr(x4), ptr(W4), ptr(b), 0, ptr(y), st), "gg_linear_fwd")
+        ctx.save_for_backward(x4, W4)
+        ctx.has_bias, ctx.K, ctx.arena, ctx.Wp, ctx.bp = b is not None, K, arena, Wp, bp
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, W = ctx.saved_tensors
+        x4, W4 = ctx.saved_tensors
         (g,) = _cuda_f32(g)
-        M, K = x.shape
-        N = W.shape[0]
+        M, K4 = x4.shape
+        N, K = W4.shape[0], ctx.K
         lib = _lib.lib()
+        dev = W4.device
         gx = None
-        dW = torch.empty_like(W)
-        db = torch.empty(N, device=W.device, dtype=torch.float32) if ctx.has_bias else None
-        with _on(g, x, W) as st:
+        dW4 = _grad_out(ctx.arena if K4 == K else None, ctx.Wp, (N, K4), dev)
+        db = _grad_out(ctx.arena, ctx.bp, (N,), dev) if ctx.has_bias else None
+        with _on(g, x4, W4) as st:
             if ctx.needs_input_grad[0]:
-                gx = torch.empty_like(x)
-                check(lib.gg_linear_bwd_data(M, N, K, ptr(g), ptr(W), None, None, ptr(gx), st), "gg_linear_bwd_data")
-            check(lib.gg_linear_bwd_weight(M, N, K, ptr(g), ptr(x), ptr(dW), ptr(db), st), "gg_linear_bwd_weight")
-        return gx, dW, db
+                gx4 = torch.empty_like(x4)
+                check(lib.gg_linear_bwd_data(M, N, K4, ptr(g), ptr(W4), None, None, ptr(gx4), st), "gg_linear_bwd_data")
+                gx = gx4 if K4 == K else gx4[:, :K].contiguous()
+            check(lib.gg_linear_bwd_weight(M, N, K4, ptr(g), ptr(x4), ptr(dW4), ptr(db), st), "gg_linear_bwd_weight")
+        if K4 != K:
+            dW = _grad_out(ctx.arena, ctx.Wp, (N, K), dev)
+            dW.copy_(dW4[:, :K])
+        else:
+            dW = dW4
+        return gx, dW, db, None, None, None
 
 
-def _pad_k(x, W):
-    """The kernels want K % 4 == 0: zero-pad the reduction dimension (18 -> 20, 2 -> 4)."""
-    K = W.shape[1]
-    r = (-K) % 4
-    if r:
-        x = F.pad(x, (0, r))
-        W = F.pad(W, (0, r))
-    return x, W
-
-
-def linear(x, W, b=None):
+def linear(x, W, b=None, arena=None):
     """nn.Linear forward (models/full_graph.py:23) on the FFMA GEMM kernel."""
-    x, W = _pad_k(x, W)
-    return _Linear.apply(x, W, b)
+    return _Linear.apply(x, W, b, arena, W, b)
 
 
 class _EdgeMLP(torch.autograd.Function):
     """linear2_edge(relu(linear1_edge(e)))  (models/full_graph.py:24-26); ReLU fused in both directions."""
 
     @staticmethod
-    def forward(ctx, e, W1, b1, W2, b2):
+    def forward(ctx, e, W1, b1, W2, b2, arena, params):
         e, W1, b1, W2, b2 = _cuda_f32(e, W1, b1, W2, b2)
         lib = _lib.lib()
         E, K = e.shape
+        K4 = (K + 3) & ~3
+        e4, W14 = _pad_cols(e, K4), _pad_cols(W1, K4)
         Hh, d = W1.shape[0], W2.shape[0]
         hid = torch.empty(E, Hh, device=e.device, dtype=torch.float32)
         out = torch.empty(E, d, device=e.device, dtype=torch.float32)
-        with _on(e, W1, b1, W2, b2) as st:
-            check(lib.gg_linear_fwd(E, Hh, K, ptr(e), ptr(W1), ptr(b1), 1, ptr(hid), st), "gg_linear_fwd")
+        with _on(e4, W14, b1, W2, b2) as st:
+            check(lib.gg_linear_fwd(E, Hh, K4, ptr(e4), ptr(W14), ptr(b1), 1, ptr(hid), st), "gg_linear_fwd")
             check(lib.gg_linear_fwd(E, d, Hh, ptr(hid), ptr(W2), ptr(b2), 0, ptr(out), st), "gg_linear_fwd")
-        ctx.save_for_backward(e, W1, W2, hid)
+        ctx.save_for_backward(e4, W14, W2, hid)
+        ctx.K, ctx.arena, ctx.params = K, arena, params
         return out
 
     @staticmethod
     def backward(ctx, g):
-        e, W1, W2, hid = ctx.saved_tensors
+        e4, W14, W2, hid = ctx.saved_tensors
         (g,) = _cuda_f32(g)
         lib = _lib.lib()
-        E, K = e.shape
-        Hh, d = W1.shape[0], W2.shape[0]
-        dW2 = torch.empty_like(W2)
-        db2 = torch.empty(d, device=g.device, dtype=torch.float32)
-        dW1 = torch.empty_like(W1)
-        db1 = torch.empty(Hh, device=g.device, dtype=torch.float32)
-        with _on(g, e, W1, W2, hid) as st:
-            if Hh == 16 and K == 4 and d in (64, 128):
+        E, K4 = e4.shape
+        K = ctx.K
+        Hh, d = W14.shape[0], W2.shape[0]
+        dev = g.device
+        pW1, pb1, pW2, pb2 = ctx.params
+        dW2 = _grad_out(ctx.arena, pW2, (d, Hh), dev)
+        db2 = _grad_out(ctx.arena, pb2, (d,), dev)
+        dW14 = _grad_out(ctx.arena if K4 == K else None, pW1, (Hh, K4), dev)
+        db1 = _grad_out(ctx.arena, pb1, (Hh,), dev)
+        with _on(g, e4, W14, W2, hid) as st:
+            if Hh == 16 and K4 == 4 and d in (64, 128):
                 # one pass over g: dW2, db2, the ReLU-masked hidden gradient (never stored), dW1, db1
-                check(lib.gg_edge_mlp_bwd(E, d, Hh, K, ptr(g), ptr(hid), ptr(e), ptr(W2), ptr(dW1), ptr(db1), ptr(dW2),
+                check(lib.gg_edge_mlp_bwd(E, d, Hh, K4, ptr(g), ptr(hid), ptr(e4), ptr(W2), ptr(dW14), ptr(db1), ptr(dW2),
                                           ptr(db2), st), "gg_edge_mlp_bwd")
-                return None, dW1, db1, dW2, db2
-            check(lib.gg_linear_bwd_weight(E, d, Hh, ptr(g), ptr(hid), ptr(dW2), ptr(db2), st), "gg_linear_bwd_weight")
-            g_hid = torch.empty_like(hid)
-            check(lib.gg_linear_bwd_data(E, d, Hh, ptr(g), ptr(W2), None, ptr(hid), ptr(g_hid), st), "gg_linear_bwd_data")
-            check(lib.gg_linear_bwd_weight(E, Hh, K, ptr(g_hid), ptr(e), ptr(dW1), ptr(db1), st), "gg_linear_bwd_weight")
-        return None, dW1, db1, dW2, db2
+            else:
+                check(lib.gg_linear_bwd_weight(E, d, Hh, ptr(g), ptr(hid), ptr(dW2), ptr(db2), st), "gg_linear_bwd_weight")
+                g_hid = torch.empty_like(hid)
+                check(lib.gg_linear_bwd_data(E, d, Hh, ptr(g), ptr(W2), None, ptr(hid), ptr(g_hid), st), "gg_linear_bwd_data")
+                check(lib.gg_linear_bwd_weight(E, Hh, K4, ptr(g_hid), ptr(e4), ptr(dW14), ptr(db1), st), "gg_linear_bwd_weight")
+        if K4 != K:
+            dW1 = _grad_out(ctx.arena, pW1, (Hh, K), dev)
+            dW1.copy_(dW14[:, :K])
+        else:
+            dW1 = dW14
+        return None, dW1, db1, dW2, db2, None, None
 
 
-def edge_mlp(e, W1, b1, W2, b2):
-    e, W1 = _pad_k(e, W1)
-    return _EdgeMLP.apply(e, W1, b1, W2, b2)
+def edge_mlp(e, W1, b1, W2, b2, arena=None):
+    return _EdgeMLP.apply(e, W1, b1, W2, b2, arena, (W1, b1, W2, b2))
 
 
 # ----------------------------------------------------------------------------------- GatedGCN layer
 class _GatedGCNLayer(torch.autograd.Function):
-    """GatedGCN_1d.forward (layers/gated_gcn_full.py:99-157); e in INTERNAL edge order."""
+    """GatedGCN_1d.forward (layers/gated_gcn_full.py:99-157); e in INTERNAL edge order.
+
+    The five node projections A_1, A_2, A_3, B_1, B_2 enter twice: as the individual parameters (w5, b5: what autograd
+    tracks and what receives the gradients) and stacked as Wn [5d, d] / bn [5d] (what the kernel reads) — views of the
+    flat parameter buffer (flat.py), no copy."""
 
     @staticmethod
-    def forward(ctx, plan, norm_kind, residual, h, e, Wn, bn, B3, b3, ge, be, gh, bh):
+    def forward(ctx, plan, norm_kind, residual, arena, conv, h, e, Wn, bn, *params):
+        # params = A1w, A2w, A3w, B1w, B2w, A1b, A2b, A3b, B1b, B2b, B3, b3, ge, be, gh, bh   (autograd inputs)
+        B3, b3, ge, be, gh, bh = params[10:]
         h, e, Wn, bn, B3, b3, ge, be, gh, bh = _cuda_f32(h, e, Wn, bn, B3, b3, ge, be, gh, bh)
         N, d = h.shape
         E = e.shape[0]
@@ -203,14 +233,14 @@ class _GatedGCNLayer(torch.autograd.Function):
             check(_lib.lib().gg_layer_fwd(plan.handle, d, norm_kind, int(residual), ptr(h), ptr(e), ptr(Wn), ptr(bn),
                                           ptr(B3), ptr(b3), ptr(ge), ptr(be), ptr(gh), ptr(bh), ptr(h_out), ptr(e_out),
                                           ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), st), "gg_layer_fwd")
-        ctx.plan, ctx.norm_kind, ctx.residual = plan, norm_kind, int(residual)
+        ctx.plan, ctx.norm_kind, ctx.residual, ctx.arena, ctx.conv = plan, norm_kind, int(residual), arena, conv
         ctx.save_for_backward(h, e, e_out, Wn, B3, ge, be, gh, bh, P, t, z, agg, stats)
         return h_out, e_out
 
     @staticmethod
     def backward(ctx, g_h, g_e):
         h, e, e_out, Wn, B3, ge, be, gh, bh, P, t, z, agg, stats = ctx.saved_tensors
-        plan = ctx.plan
+        plan, arena, conv = ctx.plan, ctx.arena, ctx.conv
         N, d = h.shape
         E = e.shape[0]
         dev = h.device
@@ -220,9 +250,19 @@ class _GatedGCNLayer(torch.autograd.Function):
         g_h_in, g_eo = torch.empty(N, d, **f32), torch.empty(E, d, **f32)
         g_t, g_e_in = torch.empty(E, d, **f32), torch.empty(E, d, **f32)
         gP, G = torch.empty(N, 5 * d, **f32), torch.empty(2, N, 2 * d, **f32)
-        dWn, dbn = torch.empty(5 * d, d, **f32), torch.empty(5 * d, **f32)
-        dB3, db3 = torch.empty(d, d, **f32), torch.empty(d, **f32)
-        dge, dbe, dgh, dbh = (torch.empty(d, **f32) for _ in range(4))
+        if arena is not None and conv is not None and id(conv.A_1.weight) in arena.layout.offset_of:
+            # flat layout of a layer (flat._layer_param_order): 5 weights | 5 biases | B3 | b3 | bn_e w,b | bn_h w,b
+            dWn = arena.slot(conv.A_1.weight, rows=5 * d * d).view(5 * d, d)
+            dbn = arena.slot(conv.A_1.bias, rows=5 * d)
+        else:
+            dWn, dbn = torch.empty(5 * d, d, **f32), torch.empty(5 * d, **f32)
+        pc = conv if conv is not None else None
+        dB3 = _grad_out(arena, pc.B_3.weight if pc else None, (d, d), dev)
+        db3 = _grad_out(arena, pc.B_3.bias if pc else None, (d,), dev)
+        dge = _grad_out(arena, pc.bn_e.weight if pc else None, (d,), dev)
+        dbe = _grad_out(arena, pc.bn_e.bias if pc else None, (d,), dev)
+        dgh = _grad_out(arena, pc.bn_h.weight if pc else None, (d,), dev)
+        dbh = _grad_out(arena, pc.bn_h.bias if pc else None, (d,), dev)
         bstats = torch.empty(4 * d, device=dev, dtype=torch.float64)
         with _on(h, e, g_h, g_e, plan=plan) as st:
             check(_lib.lib().gg_layer_bwd(
@@ -230,32 +270,51 @@ class _GatedGCNLayer(torch.autograd.Function):
                 ptr(be), ptr(gh), ptr(bh), ptr(P), ptr(t), ptr(z), ptr(agg), ptr(stats), ptr(g_h), ptr(g_e),
                 ptr(g_h_in), ptr(g_e_in), ptr(dWn), ptr(dbn), ptr(dB3), ptr(db3), ptr(dge), ptr(dbe), ptr(dgh), ptr(dbh),
                 ptr(gP), ptr(G), ptr(g_eo), ptr(g_t), ptr(bstats), st), "gg_layer_bwd")
-        return None, None, None, g_h_in, g_e_in, dWn, dbn, dB3, db3, dge, dbe, dgh, dbh
+        if arena is not None and conv is not None:
+            arena.segment_done(getattr(conv, "_gg_segment", None))
+        dws = tuple(dWn[k * d:(k + 1) * d] for k in range(5))
+        dbs = tuple(dbn[k * d:(k + 1) * d] for k in range(5))
+        return (None, None, None, None, None, g_h_in, g_e_in, None, None, *dws, *dbs, dB3, db3, dge, dbe, dgh, dbh)
 
 
-def gated_gcn_layer(plan, norm_kind, residual, h, e, Wn, bn, B3, b3, ge, be, gh, bh):
-    return _GatedGCNLayer.apply(plan, norm_kind, residual, h, e, Wn, bn, B3, b3, ge, be, gh, bh)
+def gated_gcn_layer(plan, norm_kind, residual, h, e, conv, arena=None):
+    """One layer on the parameters of `conv` (a layers.GatedGCN_1d)."""
+    from .flat import packed_node_weights
+    packed = packed_node_weights(conv)
+    ws = (conv.A_1.weight, conv.A_2.weight, conv.A_3.weight, conv.B_1.weight, conv.B_2.weight)
+    bs = (conv.A_1.bias, conv.A_2.bias, conv.A_3.bias, conv.B_1.bias, conv.B_2.bias)
+    if packed is None:                       # parameters not in a flat buffer (should not happen after ensure_flat)
+        with torch.no_grad():
+            packed = torch.cat(ws, 0), torch.cat(bs, 0)
+    Wn, bn = packed
+    return _GatedGCNLayer.apply(plan, norm_kind, residual, arena, conv, h, e, Wn, bn, *ws, *bs, conv.B_3.weight,
+                                conv.B_3.bias, conv.bn_e.weight, conv.bn_e.bias, conv.bn_h.weight, conv.bn_h.bias)
 
 
 # ----------------------------------------------------------------------------------- score predictor
 class _Score(torch.autograd.Function):
-    """ScorePredictor (layers/score_predictor.py:12-25) with W1 split by columns; internal edge order."""
+    """ScorePredictor (layers/score_predictor.py:12-25) with W1 split by columns; internal edge order.
+    W1 [H, 3d] = [W1s | W1d | W1e]: Wq = [W1s ; W1d] stacked by rows, bq = [b1 ; 0] (b1 rides on the src half of Q)."""
 
     @staticmethod
-    def forward(ctx, plan, x, e, Wq, bq, W1e, w2, b2):
-        x, e, Wq, bq, W1e, w2, b2 = _cuda_f32(x, e, Wq, bq, W1e, w2, b2)
+    def forward(ctx, plan, x, e, W1, b1, W2, b2, arena, params):
+        x, e, W1, b1, W2, b2 = _cuda_f32(x, e, W1, b1, W2, b2)
         N, d = x.shape
         E = e.shape[0]
-        H = W1e.shape[0]
+        H = W1.shape[0]
         dev = x.device
         f32 = dict(device=dev, dtype=torch.float32)
+        Wq = torch.cat((W1[:, :d], W1[:, d:2 * d]), dim=0)
+        bq = torch.cat((b1, torch.zeros_like(b1)), dim=0)
+        W1e = W1[:, 2 * d:].contiguous()
+        w2 = W2.reshape(-1)
         score, Q = torch.empty(E, **f32), torch.empty(N, 2 * H, **f32)
         need_grad = any(ctx.needs_input_grad)
         hid = torch.empty(E, H, **f32) if need_grad else None
         with _on(x, e, Wq, bq, W1e, w2, b2, plan=plan) as st:
             check(_lib.lib().gg_score_fwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(bq), ptr(W1e), ptr(w2), ptr(b2),
                                           ptr(score), ptr(Q), ptr(hid), st), "gg_score_fwd")
-        ctx.plan = plan
+        ctx.plan, ctx.arena, ctx.params = plan, arena, params
         if need_grad:
             ctx.save_for_backward(x, e, Wq, W1e, w2, hid)
         return score
@@ -264,7 +323,8 @@ class _Score(torch.autograd.Function):
     def backward(ctx, g):
         x, e, Wq, W1e, w2, hid = ctx.saved_tensors
         (g,) = _cuda_f32(g)
-        plan = ctx.plan
+        plan, arena = ctx.plan, ctx.arena
+        pW1, pb1, pW2, pb2 = ctx.params
         N, d = x.shape
         E = e.shape[0]
         H = W1e.shape[0]
@@ -272,7 +332,8 @@ class _Score(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         g_x, g_e = torch.empty(N, d, **f32), torch.empty(E, d, **f32)
         dWq, dbq, dW1e = torch.empty(2 * H, d, **f32), torch.empty(2 * H, **f32), torch.empty(H, d, **f32)
-        dw2, db2 = torch.empty(H, **f32), torch.empty(1, **f32)
+        dw2 = _grad_out(arena, pW2, (H,), dev)
+        db2 = _grad_out(arena, pb2, (1,), dev)
         gQ = torch.empty(N, 2 * H, **f32)
         red = torch.empty(2 * H + 1, device=dev, dtype=torch.float64)
         gpre = torch.empty_like(hid)
@@ -280,13 +341,14 @@ class _Score(torch.autograd.Function):
             check(_lib.lib().gg_score_bwd(plan.handle, d, H, ptr(x), ptr(e), ptr(Wq), ptr(W1e), ptr(w2), ptr(g), ptr(hid),
                                           ptr(g_x), ptr(g_e), ptr(dWq), ptr(dbq), ptr(dW1e), ptr(dw2), ptr(db2), ptr(gpre),
                                           ptr(gQ), ptr(red), st), "gg_score_bwd")
-        return None, g_x, g_e, dWq, dbq, dW1e, dw2, db2
+        dW1 = _grad_out(arena, pW1, (H, 3 * d), dev)
+        dW1[:, :d].copy_(dWq[:H])
+        dW1[:, d:2 * d].copy_(dWq[H:])
+        dW1[:, 2 * d:].copy_(dW1e)
+        db1 = _grad_out(arena, pb1, (H,), dev)
+        db1.copy_(dbq[:H])
+        return None, g_x, g_e, dW1, db1, dw2.view(1, H), db2, None, None
 
 
-def score_predictor(plan, x, e, W1, b1, W2, b2):
-    """W1 [H, 3d] -> Wq = [W1[:, :d] ; W1[:, d:2d]], W1e = W1[:, 2d:]; b1 rides on the src half of Q."""
-    d = x.shape[1]
-    Wq = torch.cat((W1[:, :d], W1[:, d:2 * d]), dim=0)
-    bq = torch.cat((b1, torch.zeros_like(b1)), dim=0)
-    W1e = W1[:, 2 * d:].contiguous()
-    return _Score.apply(plan, x, e, Wq, bq, W1e, W2.reshape(-1), b2.reshape(-1))
+def score_predictor(plan, x, e, W1, b1, W2, b2, arena=None):
+    return _Score.apply(plan, x, e, W1, b1, W2, b2, arena, (W1, b1, W2, b2))

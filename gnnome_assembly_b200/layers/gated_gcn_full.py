@@ -38,21 +38,17 @@ class GatedGCN_1d(nn.Module):
             self.bn_h = nn.LayerNorm(out_channels)
             self.bn_e = nn.LayerNorm(out_channels)
 
-    def _packed(self):
-        Wn = torch.cat((self.A_1.weight, self.A_2.weight, self.A_3.weight, self.B_1.weight, self.B_2.weight), 0)
-        bn = torch.cat((self.A_1.bias, self.A_2.bias, self.A_3.bias, self.B_1.bias, self.B_2.bias), 0)
-        return Wn, bn
-
-    def forward_internal(self, plan, h, e):
-        """h [N,d], e [E,d] in the plan's internal edge order."""
+    def forward_internal(self, plan, h, e, arena=None):
+        """h [N,d], e [E,d] in the plan's internal node / edge order.  arena: the pass's flat.GradArena (model seam)."""
         if self.dropout and self.training:
             raise NotImplementedError("dropout > 0 is never used on the reference path (processor.py:12)")
-        Wn, bn = self._packed()
         norm = GF.NORM_BATCH if self.batch_norm else GF.NORM_LAYER
-        return GF.gated_gcn_layer(plan, norm, self.residual, h, e, Wn, bn, self.B_3.weight, self.B_3.bias,
-                                  self.bn_e.weight, self.bn_e.bias, self.bn_h.weight, self.bn_h.bias)
+        return GF.gated_gcn_layer(plan, norm, self.residual, h, e, self, arena)
 
     def forward(self, g, h, e):
+        from ..flat import ensure_flat, packed_node_weights
+        if packed_node_weights(self) is None:              # stand-alone layer: its own flat parameter buffer
+            ensure_flat(self)
         plan = plan_for(g, h.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)
         h, e_int = self.forward_internal(plan, GF.permute_rows(h, plan.node_perm, plan.node_inv), e_int)

@@ -13,12 +13,14 @@ class GraphGatedGCN(nn.Module):
             GatedGCN_1d(hidden_features, hidden_features, batch_norm) for _ in range(num_layers)
         ])
 
-    def forward_internal(self, plan, h, e):
+    def forward_internal(self, plan, h, e, arena=None):
         for conv in self.convs:
-            h, e = conv.forward_internal(plan, h, e)
+            h, e = conv.forward_internal(plan, h, e, arena)
         return h, e
 
     def forward(self, graph, h, e):
+        from ..flat import ensure_flat
+        ensure_flat(self)
         plan = plan_for(graph, h.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)      # once for the whole stack
         h, e_int = self.forward_internal(plan, GF.permute_rows(h, plan.node_perm, plan.node_inv), e_int)

@@ -17,9 +17,9 @@ class ScorePredictor(nn.Module):
         self.W1 = nn.Linear(3 * in_features, hidden_edge_scores)
         self.W2 = nn.Linear(hidden_edge_scores, 1)
 
-    def forward_internal(self, plan, x, e):
+    def forward_internal(self, plan, x, e, arena=None):
         """e in internal order -> scores [E] in internal order."""
-        return GF.score_predictor(plan, x, e, self.W1.weight, self.W1.bias, self.W2.weight, self.W2.bias)
+        return GF.score_predictor(plan, x, e, self.W1.weight, self.W1.bias, self.W2.weight, self.W2.bias, arena)
 
     def forward(self, graph, x, e):
         plan = plan_for(graph, x.device)

@@ -5,10 +5,12 @@ strict=True), same `forward(graph, x, e, pe) -> scores [E, 1]` in the caller's e
 the primary seam of the engine: inside, everything runs in the plan's internal (dst-sorted) edge order;
 only the E x 2 input and the E x 1 output are permuted.
 """
+import torch
 import torch.nn as nn
 
 from .. import functional as GF
 from .. import layers
+from ..flat import GradArena, ensure_flat
 from ..plan import plan_for
 
 
@@ -21,14 +23,23 @@ class GraphGatedGCNModel(nn.Module):
         self.linear2_edge = nn.Linear(hidden_edge_features, hidden_features)
         self.gnn = layers.GraphGatedGCN(num_layers, hidden_features, batch_norm)
         self.predictor = layers.ScorePredictor(hidden_features, hidden_edge_scores)
+        self.arena_hook = None            # callable(GradArena), set by the data-parallel gradient sync (dp.ArenaSync)
+        self._gg_last_arena = None
 
     def forward(self, graph, x, e, pe):
+        layout = ensure_flat(self)                                                  # parameters as views of one buffer
+        arena = None
+        if torch.is_grad_enabled() and layout is not None:
+            arena = GradArena(layout, pe.device)                                   # this pass's gradient buffer
+            self._gg_last_arena = arena
+            if self.arena_hook is not None:
+                self.arena_hook(arena)                                             # dp.ArenaSync attaches here
         plan = plan_for(graph, pe.device)
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)                       # E x 2, edge-id -> internal
         pe = GF.permute_rows(pe, plan.node_perm, plan.node_inv)                    # N x 18, node id -> internal
-        h = GF.linear(pe, self.linear_pe.weight, self.linear_pe.bias)              # full_graph.py:23 (x ignored)
+        h = GF.linear(pe, self.linear_pe.weight, self.linear_pe.bias, arena)       # full_graph.py:23 (x ignored)
         e_int = GF.edge_mlp(e_int, self.linear1_edge.weight, self.linear1_edge.bias,
-                            self.linear2_edge.weight, self.linear2_edge.bias)      # :24-26
-        h, e_int = self.gnn.forward_internal(plan, h, e_int)                       # :27
-        s = self.predictor.forward_internal(plan, h, e_int)                        # :28
+                            self.linear2_edge.weight, self.linear2_edge.bias, arena)   # :24-26
+        h, e_int = self.gnn.forward_internal(plan, h, e_int, arena)                # :27
+        s = self.predictor.forward_internal(plan, h, e_int, arena)                 # :28
         return GF.permute_rows(s.unsqueeze(-1), plan.inv_perm, plan.perm)          # internal -> edge-id, [E,1]

@@ -165,6 +165,95 @@ def test_grad_bucket_allreduce_gloo_world2():
         assert torch.allclose(b, torch.full((3, 4), 2.0))
 
 
+def _arena_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200.dp import ArenaSync
+    from gnnome_assembly_b200.flat import GradArena, ensure_flat
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = gg.GraphGatedGCNModel(1, 2, 64, 16, 2, 64, True, 16)          # host-resident: only the sync logic runs
+    sync = ArenaSync(model)
+    layout = ensure_flat(model)
+
+    def fake_backward(value):
+        """what a backward pass does to the arena: fill, hand autograd-style views to .grad, signal the layers"""
+        arena = GradArena(layout, torch.device("cpu"))
+        model.arena_hook(arena)
+        arena.tensor().fill_(value)
+        for p, off in layout.entries:
+            p.grad = arena.tensor()[off:off + p.numel()].view_as(p)
+        arena.segment_done("conv1")                                         # backward order: last layer first
+        arena.segment_done("conv0")
+        return arena
+
+    sync.begin(world)
+    fake_backward(float(rank + 1))
+    sync.finish()
+    a = [float(p.grad.flatten()[0]) for p in model.parameters()]
+    # short wave: rank 1 idle, divisor = 1 active rank
+    sync.begin(1)
+    if rank == 0:
+        fake_backward(5.0)
+        sync.finish()
+    else:
+        sync.idle_step()
+    b = [float(p.grad.flatten()[0]) for p in model.parameters()]
+    q.put((rank, a, b))
+    dist.destroy_process_group()
+
+
+def test_arena_sync_gloo_world2():
+    """dp.ArenaSync: per-segment all-reduce of the flat gradient arena (layer segments as their backward finishes, the
+    head segment in finish), mean over the active ranks, an idle rank of a short wave walks the same collectives."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_arena_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for _, a, b in res:
+        assert all(abs(x - 1.5) < 1e-6 for x in a) and len(a) == 42          # mean of 1 and 2, every parameter
+        assert all(abs(x - 5.0) < 1e-6 for x in b)                           # rank 0's gradient alone, on both ranks
+
+
+def test_flat_parameters_keep_the_reference_state_dict():
+    """flat.ensure_flat: parameters become views of one buffer (Wn / bn are strided views, no cat), values, names and
+    shapes of the state_dict are untouched, deep copies and load_state_dict keep working."""
+    import copy
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200.flat import GradArena, ensure_flat, packed_node_weights
+    torch.manual_seed(1)
+    m = gg.GraphGatedGCNModel(1, 2, 64, 16, 2, 64, True, 16)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    layout = ensure_flat(m)
+    assert [n for n, _, _ in layout.segments] == ["head", "conv0", "conv1"]
+    assert list(m.state_dict().keys()) == list(sd0.keys())
+    assert all(torch.equal(sd0[k], v) for k, v in m.state_dict().items())
+    c = m.gnn.convs[1]
+    Wn, bn = packed_node_weights(c)
+    assert torch.equal(Wn, torch.cat([c.A_1.weight, c.A_2.weight, c.A_3.weight, c.B_1.weight, c.B_2.weight], 0))
+    assert torch.equal(bn, torch.cat([c.A_1.bias, c.A_2.bias, c.A_3.bias, c.B_1.bias, c.B_2.bias], 0))
+    assert Wn.data_ptr() == c.A_1.weight.data_ptr()                          # a view, not a copy
+    assert ensure_flat(m) is layout                                          # idempotent
+    with torch.no_grad():
+        c.A_3.weight.add_(1.0)                                               # an optimizer update through the parameter
+    assert torch.equal(packed_node_weights(c)[0][128:192], c.A_3.weight)     # ... is seen by the packed view
+    m2 = copy.deepcopy(m)                                                    # train.py:199-206 keeps a best_model copy
+    assert ensure_flat(m2) is not layout and packed_node_weights(m2.gnn.convs[0]) is not None
+    m.load_state_dict(sd0, strict=True)
+    assert ensure_flat(m) is layout and torch.equal(c.A_3.weight, sd0["gnn.convs.1.A_3.weight"])
+    arena = GradArena(layout, torch.device("cpu"))
+    assert arena.slot(c.A_1.weight, rows=5 * 64 * 64).numel() == 5 * 64 * 64
+    assert arena.slot(c.bn_h.bias).data_ptr() == arena.tensor().data_ptr() + 4 * layout.offset_of[id(c.bn_h.bias)]
+
+
 # ------------------------------------------------------------------------------------------ graph files, dgl stand-in
 def test_graph_file_round_trip(tmp_path):
     """DGL-free graph container (graph_io.py) behind dgl.save_graphs / dgl.load_graphs (graph_dataset.py:72,129)."""
