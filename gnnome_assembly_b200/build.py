@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -195,7 +195,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   GG_KERNEL_END("node_bwd_reduce_kernel", st);
   GG_KERNEL_BEGIN("node_bwd_apply_kernel", st);
   node_bwd_apply_kernel<D, NORM><<<node_grid(node_bwd_apply_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, bstats, gamma_h, beta_h,
-                                                               agg, gP, G);
+                                                               agg, gP, G, dgamma_h, dbeta_h);
   GG_KERNEL_END("node_bwd_apply_kernel", st);
   GG_KERNEL_BEGIN("edge_bwd_a_kernel", st);
   edge_bwd_a_kernel<D, NORM><<<node_grid(edge_bwd_a_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
@@ -222,7 +222,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   GG_KERNEL_BEGIN("edge_bwd_src_kernel", st);
   edge_bwd_src_kernel<D><<<node_grid(edge_bwd_src_kernel<D>, N), kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP,
                                                        fused_gt ? 1 : 0, E, pl->in_ptr, agg + 4 * N * D, stats,
-                                                       bstats + 2 * D, gamma_e);
+                                                       bstats + 2 * D, gamma_e, dgamma_e, dbeta_e);
   GG_KERNEL_END("edge_bwd_src_kernel", st);
   // g_e_in = g_eo (residual) + g_t B3 ; dB3 = g_t^T e_in ; db3 = colsum g_t
   if (!fused_gt) {
@@ -236,12 +236,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   if (rc) return rc;
   rc = linear_bwd_weight("gemm_dWn", N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, st);
   if (rc) return rc;
-  GG_KERNEL_BEGIN("affine_grads_kernel", st);
-  affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats, dgamma_h, dbeta_h);
-  GG_KERNEL_END("affine_grads_kernel", st);
-  GG_KERNEL_BEGIN("affine_grads_kernel", st);
-  affine_grads_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, bstats + 2 * D, dgamma_e, dbeta_e);
-  GG_KERNEL_END("affine_grads_kernel", st);
+  // (dgamma / dbeta of both norms are written by node_bwd_apply_kernel and edge_bwd_src_kernel: no launches of their own)
   return GG_OK;
 }
 
