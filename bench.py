@@ -424,7 +424,8 @@ def run_ours(args):
                     "timing": "CUDA event pair per launch on the launching stream, 3 extra steps after the timed region",
                     "algorithmic_bytes_per_launch": ab[dom]}
     step_bytes = step_algorithmic_bytes(E, N, D, L)
-    cpu_val, cpu_dt, cores, sample = cpu_oracle_rate(steps=2, warmup=1, scale=1.0) if world == 1 else (None,) * 4
+    cpu_val, cpu_dt, cores, sample = (cpu_oracle_rate(steps=2, warmup=1, scale=1.0)
+                                      if world == 1 and not args.no_baselines else (None,) * 4)
 
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
@@ -469,6 +470,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / eager-CUDA baseline legs "
+                    "(same-box A/B runs of library variants, tools/ab_bench.sh)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the first-step loss / gradient check against "
                     "the CPU oracle (about 15 s of host time)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (default: the step "

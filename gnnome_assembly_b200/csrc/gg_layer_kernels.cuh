@@ -103,6 +103,14 @@ struct CsrCursor {
   // call at the top of node v's iteration: issues the look-ahead loads (consumed by advance())
   __device__ __forceinline__ void prefetch(const int32_t* __restrict__ ptr, const int32_t* const (&arr)[kIdx], int64_t N,
                                            int64_t v, int64_t nw, int lane) {
+#ifdef GG_NO_LOOKAHEAD      // A/B builds (tools/ab_build.sh): the dependent chain of round 1
+    nbeg = 0; nend = 0;
+    if (v + nw < N) { nbeg = __ldg(ptr + v + nw); nend = __ldg(ptr + v + nw + 1); }
+    asm volatile("" ::"r"(nbeg), "r"(nend) : "memory");
+#pragma unroll
+    for (int k = 0; k < kIdx; ++k) nidx[k] = -1;
+    return;
+#endif
     nnbeg = 0; nnend = 0;
     if (v + 2 * nw < N) { nnbeg = __ldg(ptr + v + 2 * nw); nnend = __ldg(ptr + v + 2 * nw + 1); }
 #pragma unroll
@@ -110,6 +118,9 @@ struct CsrCursor {
   }
   // indices of the 32-edge block starting at `base` of the current node (the first block is already in registers)
   __device__ __forceinline__ int block_idx(const int32_t* __restrict__ a, int k, int base, int cnt, int lane) const {
+#ifdef GG_NO_LOOKAHEAD
+    if (idx[k] < 0 || base != beg) return (lane < cnt) ? __ldg(a + base + lane) : 0;
+#endif
     return base == beg ? idx[k] : ((lane < cnt) ? __ldg(a + base + lane) : 0);
   }
   __device__ __forceinline__ void advance() {

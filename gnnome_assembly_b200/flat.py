@@ -128,6 +128,12 @@ def packed_node_weights(conv):
         return None
     if any(b.data_ptr() != b0 + 4 * d * k for k, b in enumerate(bs)):
         return None
+    # adjacent addresses are not enough (separately allocated tensors can sit back to back in the caching allocator):
+    # the five tensors must be views of ONE storage
+    st_w, st_b = ws[0].untyped_storage(), bs[0].untyped_storage()
+    if any(w.untyped_storage().data_ptr() != st_w.data_ptr() for w in ws) or \
+            any(b.untyped_storage().data_ptr() != st_b.data_ptr() for b in bs):
+        return None
     with torch.no_grad():
         Wn = torch.as_strided(ws[0].data, (5 * d, d), (d, 1))
         bn = torch.as_strided(bs[0].data, (5 * d,), (1,))
