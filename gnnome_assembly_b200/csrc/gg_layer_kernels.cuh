@@ -11,9 +11,6 @@
 namespace gg {
 
 constexpr int kNodeThreads = 256;   // 8 warps per CTA
-// resident CTAs per SM the streaming kernels are compiled for (register cap 64 / 85 / 128 per thread): the CSR look-ahead
-// must not cost a resident CTA
-template <int D> constexpr int node_min_blocks() { return D <= 64 ? 4 : (D <= 128 ? 3 : 2); }
 
 // ------------------------------------------------------------------ normalisation coefficients
 // NORM == GG_NORM_BATCH: per-channel batch statistics from fp64 sums (biased variance, eps 1e-5)
@@ -81,55 +78,10 @@ struct Norm {
   }
 };
 
-// CSR cursor with a two-node look-ahead.  A warp walks nodes v, v + nw, v + 2 nw, ...; per node the chain
-//   ptr[v] -> index array [beg ..] -> gathered rows
-// is three dependent global loads deep before the first feature row arrives (about 2 us per node under load, a third
-// of a node's time at the average degree of 8).  The cursor keeps the CSR range of the next node and of the one after
-// it in registers and fetches the first 32 indices of the NEXT node while the current one is being processed, so only
-// the row loads themselves are exposed.  kIdx = number of index arrays walked in lock step (in-edges: src; out-edges:
-// edge id + destination).
-template <int kIdx>
-struct CsrCursor {
-  int beg = 0, end = 0, nbeg = 0, nend = 0, nnbeg = 0, nnend = 0;
-  int idx[kIdx], nidx[kIdx];
-  // (the array pointers are kernel parameters: passing them per call keeps them in the constant bank, not in registers)
-  __device__ __forceinline__ void init(const int32_t* __restrict__ ptr, const int32_t* const (&arr)[kIdx], int64_t N,
-                                       int64_t v, int64_t nw, int lane) {
-    if (v < N) { beg = __ldg(ptr + v); end = __ldg(ptr + v + 1); }
-    if (v + nw < N) { nbeg = __ldg(ptr + v + nw); nend = __ldg(ptr + v + nw + 1); }
-#pragma unroll
-    for (int k = 0; k < kIdx; ++k) { idx[k] = (beg + lane < end) ? __ldg(arr[k] + beg + lane) : 0; nidx[k] = 0; }
-  }
-  // call at the top of node v's iteration: issues the look-ahead loads (consumed by advance())
-  __device__ __forceinline__ void prefetch(const int32_t* __restrict__ ptr, const int32_t* const (&arr)[kIdx], int64_t N,
-                                           int64_t v, int64_t nw, int lane) {
-#ifdef GG_NO_LOOKAHEAD      // A/B builds (tools/ab_build.sh): the dependent chain of round 1
-    nbeg = 0; nend = 0;
-    if (v + nw < N) { nbeg = __ldg(ptr + v + nw); nend = __ldg(ptr + v + nw + 1); }
-    asm volatile("" ::"r"(nbeg), "r"(nend) : "memory");
-#pragma unroll
-    for (int k = 0; k < kIdx; ++k) nidx[k] = -1;
-    return;
-#endif
-    nnbeg = 0; nnend = 0;
-    if (v + 2 * nw < N) { nnbeg = __ldg(ptr + v + 2 * nw); nnend = __ldg(ptr + v + 2 * nw + 1); }
-#pragma unroll
-    for (int k = 0; k < kIdx; ++k) nidx[k] = (nbeg + lane < nend) ? __ldg(arr[k] + nbeg + lane) : 0;
-  }
-  // indices of the 32-edge block starting at `base` of the current node (the first block is already in registers)
-  __device__ __forceinline__ int block_idx(const int32_t* __restrict__ a, int k, int base, int cnt, int lane) const {
-#ifdef GG_NO_LOOKAHEAD
-    if (idx[k] < 0 || base != beg) return (lane < cnt) ? __ldg(a + base + lane) : 0;
-#endif
-    return base == beg ? idx[k] : ((lane < cnt) ? __ldg(a + base + lane) : 0);
-  }
-  __device__ __forceinline__ void advance() {
-    beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
-#pragma unroll
-    for (int k = 0; k < kIdx; ++k) idx[k] = nidx[k];
-  }
-};
-
+// Tried in round 2 and withdrawn: a CSR cursor with a two-node look-ahead (CSR range of the next two nodes and the first
+// 32 indices of the next node fetched while the current node is processed, to take the ptr -> index -> row dependency
+// chain off the critical path).  Same-box A/B on the bench graph (profiles/r2_ab_lookahead.txt): 1-2 % SLOWER in all
+// four streaming kernels — other resident warps already hide that chain, the extra registers only add spills.
 // per-thread fp64 column accumulators -> one fp64 atomic per channel per CTA
 template <int D>
 __device__ __forceinline__ void block_flush_stats(const double (&s1)[D / 32], const double (&s2)[D / 32],
@@ -157,7 +109,7 @@ __device__ __forceinline__ void block_flush_stats(const double (&s1)[D / 32], co
 //   n = norm_e(t_i); e_out_i = relu(n) + e_in_i; sigma = sigmoid(e_out_i)           (:122-127)
 //   num_f[v] += sigma * A2h[s_i]; den_f[v] += sigma; hf = num_f / (den_f + 1e-6)      (:128-130)
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
+__global__ void __launch_bounds__(kNodeThreads)
 edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ src,
                      const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ P,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -172,17 +124,13 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
   float* hf = agg;
   float* invden_f = agg + 2 * N * D;
   float* sum_xhat = agg + 4 * N * D;      // sum over in-edges of xhat_e: lets the backward rebuild gB2h per node
-  CsrCursor<1> cur;
-  const int32_t* const carr[1] = {src};
-  cur.init(in_ptr, carr, N, gw, nw, lane);
-  for (int64_t v = gw; v < N; v += nw, cur.advance()) {
-    cur.prefetch(in_ptr, carr, N, v, nw, lane);
-    const int beg = cur.beg, end = cur.end;
+  for (int64_t v = gw; v < N; v += nw) {
+    const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> num, den, sx;
     num.fill(0.f); den.fill(0.f); sx.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      const int my_s = cur.block_idx(src, 0, base, cnt, lane);
+      const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
       for (int j = 0; j < cnt; j += 2) {
         const bool two = (j + 1) < cnt;
         const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
@@ -240,7 +188,7 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
 //   num_b[u] += sigma_i * A3h[v_i]; den_b[u] += sigma_i; hb = num_b / (den_b + 1e-6)
 //   z[u] = A1h[u] + hf[u] + hb[u]   and per-channel sum / sum of squares of z for bn_h
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
+__global__ void __launch_bounds__(kNodeThreads)
 node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ e_out,
                     const float* __restrict__ P, float* __restrict__ agg, float* __restrict__ z,
@@ -255,18 +203,14 @@ node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
   double s1[VPL], s2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
-  CsrCursor<2> cur;
-  const int32_t* const carr[2] = {out_eid, out_dst};
-  cur.init(out_ptr, carr, N, gw, nw, lane);
-  for (int64_t u = gw; u < N; u += nw, cur.advance()) {
-    cur.prefetch(out_ptr, carr, N, u, nw, lane);
-    const int beg = cur.beg, end = cur.end;
+  for (int64_t u = gw; u < N; u += nw) {
+    const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> num, den;
     num.fill(0.f); den.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      const int my_i = cur.block_idx(out_eid, 0, base, cnt, lane);
-      const int my_v = cur.block_idx(out_dst, 1, base, cnt, lane);
+      const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
+      const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
       for (int j = 0; j < cnt; j += 4) {
         // four out-edges in flight: all row gathers are issued before any math
         Row<D> eo[4], a3[4];
@@ -456,12 +400,8 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
   float f1[VPL], f2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
-  CsrCursor<1> cur;
-  const int32_t* const carr[1] = {src};
-  cur.init(in_ptr, carr, N, gw, nw, lane);
-  for (int64_t v = gw; v < N; v += nw, cur.advance()) {
-    cur.prefetch(in_ptr, carr, N, v, nw, lane);
-    const int beg = cur.beg, end = cur.end;
+  for (int64_t v = gw; v < N; v += nw) {
+    const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> gnf, gdf, a3, acc, sgn;
     acc.fill(0.f); sgn.fill(0.f);
     if (beg < end) {
@@ -489,7 +429,7 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
     };
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      const int my_s = cur.block_idx(src, 0, base, cnt, lane);
+      const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
       for (int j = 0; j < cnt; j += 2) {
         const bool two = (j + 1) < cnt;
         const int64_t i0 = base + j, i1 = two ? i0 + 1 : i0;
@@ -588,7 +528,7 @@ edge_bwd_b_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
 // With fix != 0 (batch norm, g_t produced inside the bwd-data GEMM): gP[u, 4d:5d] arrives holding
 // S = sum_{in(u)} g_n and is finished here as gB2h[u] = gamma rstd (S - indeg m1 - m2 sum_{in(u)} xhat).
 template <int D>
-__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
+__global__ void __launch_bounds__(kNodeThreads)
 edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ g_t,
                     const float* __restrict__ e_out, const float* __restrict__ G, float* __restrict__ gP,
@@ -620,18 +560,14 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
     }
   }
   const float* Gf = G;
-  CsrCursor<2> cur;
-  const int32_t* const carr[2] = {out_eid, out_dst};
-  cur.init(out_ptr, carr, N, gw, nw, lane);
-  for (int64_t u = gw; u < N; u += nw, cur.advance()) {
-    cur.prefetch(out_ptr, carr, N, u, nw, lane);
-    const int beg = cur.beg, end = cur.end;
+  for (int64_t u = gw; u < N; u += nw) {
+    const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> acc1, acc2;
     acc1.fill(0.f); acc2.fill(0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      const int my_i = cur.block_idx(out_eid, 0, base, cnt, lane);
-      const int my_v = cur.block_idx(out_dst, 1, base, cnt, lane);
+      const int my_i = (lane < cnt) ? __ldg(out_eid + base + lane) : 0;
+      const int my_v = (lane < cnt) ? __ldg(out_dst + base + lane) : 0;
       for (int j = 0; j < cnt; j += 4) {
         Row<D> gt[4], eo[4], gnf[4];
 #pragma unroll
