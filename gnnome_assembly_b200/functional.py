@@ -352,3 +352,97 @@ class _Score(torch.autograd.Function):
 
 def score_predictor(plan, x, e, W1, b1, W2, b2, arena=None):
     return _Score.apply(plan, x, e, W1, b1, W2, b2, arena, (W1, b1, W2, b2))
+
+
+# ----------------------------------------------------------------------------------- whole model, one call each way
+class _ModelDesc(_lib.C.Structure):
+    _fields_ = [(n, _lib.C.c_int32) for n in ("d", "layers", "hidden_edge", "hidden_score", "norm_kind", "node_in",
+                                               "edge_in", "reserved")]
+
+
+def model_call_table(model, layout):
+    """(descriptor, int64 offset table) of include/gnnome_b200.h's gg_model_fwd for `model` under `layout`;
+    cached on the layout (it dies with it on a re-flatten)."""
+    cached = layout.__dict__.get("_model_call")
+    if cached is not None:
+        return cached
+    C = _lib.C
+    off = layout.offset_of
+    convs = list(model.gnn.convs)
+    d = model.linear_pe.weight.shape[0]
+    table = [off[id(p)] for p in (model.linear_pe.weight, model.linear_pe.bias, model.linear1_edge.weight,
+                                  model.linear1_edge.bias, model.linear2_edge.weight, model.linear2_edge.bias,
+                                  model.predictor.W1.weight, model.predictor.W1.bias, model.predictor.W2.weight,
+                                  model.predictor.W2.bias)]
+    for c in convs:
+        table += [off[id(p)] for p in (c.A_1.weight, c.A_1.bias, c.B_3.weight, c.B_3.bias, c.bn_e.weight, c.bn_e.bias,
+                                       c.bn_h.weight, c.bn_h.bias)]
+    norm = NORM_BATCH if (not convs or convs[0].batch_norm) else NORM_LAYER
+    desc = _ModelDesc(d, len(convs), model.linear1_edge.weight.shape[0], model.predictor.W1.weight.shape[0], norm,
+                      model.linear_pe.weight.shape[1], model.linear1_edge.weight.shape[1], 0)
+    offs = (C.c_int64 * len(table))(*table)
+    layout.__dict__["_model_call"] = (desc, offs, len(table))
+    return layout.__dict__["_model_call"]
+
+
+class _Model(torch.autograd.Function):
+    """GraphGatedGCNModel.forward (models/full_graph.py:22-29) through gg_model_fwd / gg_model_bwd: the parameters are
+    read from the model's flat buffer, the gradients land in the pass's GradArena; `params` (autograd inputs, flat order)
+    only tell autograd where the gradients go."""
+
+    @staticmethod
+    def forward(ctx, model, plan, layout, flat, arena, e, pe, *params):
+        e, pe = _cuda_f32(e, pe)
+        C = _lib.C
+        desc, offs, n = model_call_table(model, layout)
+        E, N = plan.num_edges, plan.num_nodes
+        if e.shape[0] != E or pe.shape[0] != N or e.shape[1] != desc.edge_in or pe.shape[1] != desc.node_in:
+            raise RuntimeError(f"GraphGatedGCNModel: e{tuple(e.shape)} / pe{tuple(pe.shape)} do not match the graph "
+                               f"(N={N}, E={E}) or the model (edge_features={desc.edge_in}, nb_pos_enc+2={desc.node_in})")
+        training = arena is not None
+        lib = _lib.lib()
+        floats = lib.gg_model_workspace_floats(plan.handle, C.byref(desc), 0 if training else 1)
+        if floats < 0:
+            raise RuntimeError("gg_model_workspace_floats: unsupported model configuration")
+        ws = torch.empty(max(int(floats), 1), device=pe.device, dtype=torch.float32)
+        scores = torch.empty(E, 1, device=pe.device, dtype=torch.float32)
+        with _on(e, pe, flat, plan=plan) as st:
+            check(lib.gg_model_fwd(plan.handle, C.byref(desc), ptr(flat), offs, n, ptr(e), ptr(pe), int(training), ptr(ws),
+                                   ptr(scores), st), "gg_model_fwd")
+        ctx.model, ctx.plan, ctx.layout, ctx.flat, ctx.arena, ctx.params = model, plan, layout, flat, arena, params
+        ctx.save_for_backward(ws)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        (ws,) = ctx.saved_tensors
+        (g,) = _cuda_f32(g)
+        C = _lib.C
+        model, plan, layout, flat, arena = ctx.model, ctx.plan, ctx.layout, ctx.flat, ctx.arena
+        desc, offs, n = model_call_table(model, layout)
+        lib = _lib.lib()
+        L = desc.layers
+        bws = torch.empty(max(int(lib.gg_model_workspace_floats(plan.handle, C.byref(desc), 2)), 1), device=g.device,
+                          dtype=torch.float32)
+        grads = arena.tensor()
+
+        def run(lo, hi, st):
+            check(lib.gg_model_bwd(plan.handle, C.byref(desc), ptr(flat), offs, n, ptr(g), ptr(ws), ptr(bws), ptr(grads),
+                                   lo, hi, st), "gg_model_bwd")
+
+        with _on(g, ws, flat, plan=plan) as st:
+            if arena.on_segment_ready is None:
+                run(0, L + 2, st)
+            else:                                   # data-parallel sync: one phase per call, a layer's arena segment is
+                run(0, 1, st)                       # handed to the all-reduce as soon as its backward is enqueued
+                for k in range(L):
+                    run(1 + k, 2 + k, st)
+                    arena.segment_done(f"conv{L - 1 - k}")
+                run(L + 1, L + 2, st)
+        out = tuple(grads[o:o + p.numel()].view_as(p) for p, o in layout.entries)
+        return (None, None, None, None, None, None, None, *out)
+
+
+def model_forward(model, plan, layout, flat, arena, e, pe):
+    params = tuple(p for p, _ in layout.entries)
+    return _Model.apply(model, plan, layout, flat, arena, e, pe, *params)

@@ -25,16 +25,26 @@ class GraphGatedGCNModel(nn.Module):
         self.predictor = layers.ScorePredictor(hidden_features, hidden_edge_scores)
         self.arena_hook = None            # callable(GradArena), set by the data-parallel gradient sync (dp.ArenaSync)
         self._gg_last_arena = None
+        self.per_op_path = False          # True: per-op bindings instead of the one-call gg_model_fwd / gg_model_bwd
 
     def forward(self, graph, x, e, pe):
         layout = ensure_flat(self)                                                  # parameters as views of one buffer
+        flat = self.__dict__["_gg_flat"][1]
         arena = None
-        if torch.is_grad_enabled() and layout is not None:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             arena = GradArena(layout, pe.device)                                   # this pass's gradient buffer
             self._gg_last_arena = arena
             if self.arena_hook is not None:
                 self.arena_hook(arena)                                             # dp.ArenaSync attaches here
         plan = plan_for(graph, pe.device)
+        if self.per_op_path:
+            return self._forward_per_op(plan, e, pe, arena)
+        # one C-ABI call for the whole forward (gg_model_fwd), one for the backward (gg_model_bwd)
+        return GF.model_forward(self, plan, layout, flat, arena, e, pe)
+
+    def _forward_per_op(self, plan, e, pe, arena):
+        """The same forward through the per-op bindings (one autograd node per encoder / layer / predictor): the path
+        the layer-level seams use, kept here as a cross-check of the one-call path (tests)."""
         e_int = GF.permute_rows(e, plan.perm, plan.inv_perm)                       # E x 2, edge-id -> internal
         pe = GF.permute_rows(pe, plan.node_perm, plan.node_inv)                    # N x 18, node id -> internal
         h = GF.linear(pe, self.linear_pe.weight, self.linear_pe.bias, arena)       # full_graph.py:23 (x ignored)

@@ -169,6 +169,40 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
                  float* g_e, float* dWq, float* dbq, float* dW1e, float* dw2, float* db2, float* g_pre,
                  float* gQ, double* red, void* stream);
 
+/* ---- whole model in one call -------------------------------------------------------------------
+ * Replaces GraphGatedGCNModel.forward, models/full_graph.py:22-29 (linear_pe, linear1_edge -> ReLU -> linear2_edge,
+ * L x GatedGCN_1d, ScorePredictor) and its autograd: a host-side sequencer over the entry points above, so that one
+ * forward (and one backward) is ONE call issuing ~60 launches back to back instead of ~150 bound calls — what makes the
+ * reference's default cluster mini-batch path (train.py:282-312: batches of 25-40 k edges) GPU-bound instead of
+ * host-bound.  `params` is the model's FLAT fp32 parameter buffer, `offs` an int64 table of offsets (in floats) into it,
+ * n_offs = 10 + 8 * layers entries:
+ *   0 linear_pe.weight[d, node_in] 1 linear_pe.bias  2 linear1_edge.weight[he, edge_in] 3 .bias  4 linear2_edge.weight[d, he]
+ *   5 .bias  6 predictor.W1.weight[H, 3d] 7 .bias  8 predictor.W2.weight[1, H] 9 .bias
+ *   10 + 8 l + {0 Wn[5d, d] = A_1,A_2,A_3,B_1,B_2 stacked, 1 bn[5d], 2 B_3.weight, 3 B_3.bias, 4 bn_e.weight, 5 bn_e.bias,
+ *               6 bn_h.weight, 7 bn_h.bias}
+ * `grads` (gg_model_bwd) is a flat buffer addressed by the SAME table.  e[E, edge_in], pe[N, node_in] and scores[E] are in
+ * the CALLER's edge / node order (the permutation to the plan's internal order happens inside).
+ * Workspaces are caller-owned: gg_model_workspace_floats(plan, m, which) floats, which = 0 forward that keeps what the
+ * backward reads, 1 forward for inference (layer buffers reused), 2 backward scratch.  gg_model_bwd runs the phases
+ * [phase_begin, phase_end) of: 0 predictor, 1 + k layer L-1-k, L + 1 encoders — a caller that all-reduces gradients
+ * per layer issues one call per phase; 0 .. L + 2 does everything. */
+typedef struct gg_model_desc {
+  int32_t d;            /* hidden_features: 64, 128 or 256 */
+  int32_t layers;       /* num_layers */
+  int32_t hidden_edge;  /* hidden_edge_features (16) */
+  int32_t hidden_score; /* hidden_edge_scores (64) */
+  int32_t norm_kind;    /* GG_NORM_BATCH / GG_NORM_LAYER */
+  int32_t node_in;      /* nb_pos_enc + 2 */
+  int32_t edge_in;      /* edge_features (2) */
+  int32_t reserved;
+} gg_model_desc_t;
+int64_t gg_model_workspace_floats(const gg_plan_t* plan, const gg_model_desc_t* m, int which);
+int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* params, const int64_t* offs, int n_offs,
+                 const float* e, const float* pe, int training, float* ws, float* scores, void* stream);
+int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* params, const int64_t* offs, int n_offs,
+                 const float* g_scores, const float* ws, float* bws, float* grads, int phase_begin, int phase_end,
+                 void* stream);
+
 /* ---- input preparation ("next" row 1 of SURVEY.md 8f) ----------------------------------------------
  * gg_prep_edge_features replaces utils.preprocess_graph, utils.py:70-74: e[E,2] = z-scored overlap_length,
  * overlap_similarity (mean / unbiased std per graph), caller edge order in and out.  ws: 4 doubles.

@@ -209,3 +209,66 @@ def test_training_trajectory_tc_equals_ffma(chr19_graph):
     assert all(np.isfinite(a)) and a[-1] < a[0]
     for x, y_ in zip(a, b):
         assert abs(x - y_) < 1e-4 * max(1.0, abs(y_)), (a, b)
+
+
+@pytest.mark.parametrize("d,L,bn", [(64, 2, True), (128, 3, True), (128, 2, False), (256, 2, True)])
+def test_one_call_model_path_equals_per_op_path(d, L, bn):
+    """gg_model_fwd / gg_model_bwd (one C-ABI call per direction, gradients into the flat arena) against the per-op
+    bindings (one autograd node per encoder / layer / predictor): same kernels in the same order, so logits and every
+    gradient agree to fp64-atomic reordering noise; and both against the CPU oracle."""
+    dev = _dev()
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200.synth import make_assembly_graph
+    from oracle.gatedgcn_oracle import OracleModel, bce_loss, grads_close, rel_err
+    g = make_assembly_graph("chr19", seed=11, genome_len=2_000_000)
+    src, dst, e, pe, y = _graph_tensors(g)
+    graph = gg.AssemblyGraph(src, dst, g.num_nodes)
+    torch.manual_seed(d + L)
+    oracle = OracleModel(1, 2, d, 16, L, 64, bn, 16)
+    outs = {}
+    for per_op in (False, True):
+        model = gg.GraphGatedGCNModel(1, 2, d, 16, L, 64, bn, 16)
+        model.load_state_dict(oracle.state_dict(), strict=True)
+        model.to(dev)
+        model.per_op_path = per_op
+        s = model(graph, None, e.to(dev), pe.to(dev))
+        bce_loss(s, y.to(dev), 1 / 16.5).backward()
+        outs[per_op] = (s.detach(), {k: p.grad.clone() for k, p in model.named_parameters()})
+        with torch.no_grad():
+            s_inf = model(graph, None, e.to(dev), pe.to(dev))              # inference layout of the workspace
+        assert rel_err(s_inf, s) < 1e-6
+    assert rel_err(outs[False][0], outs[True][0]) < 1e-6
+    assert grads_close(outs[False][1], outs[True][1], rtol=1e-5, atol_frac=1e-6) == []
+    r = oracle(src, dst, g.num_nodes, e, pe)
+    bce_loss(r, y, 1 / 16.5).backward()
+    assert rel_err(outs[False][0], r) < TOL
+    assert grads_close(outs[False][1], {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5) == []
+
+
+def test_gradients_live_in_the_arena_and_survive_a_second_pass():
+    """flat.GradArena: after backward every .grad IS its slot of the pass's arena (no copies); a second forward/backward
+    gets a fresh arena, so gradients of the first pass are not overwritten behind the caller's back."""
+    dev = _dev()
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200.synth import make_assembly_graph
+    from oracle.gatedgcn_oracle import bce_loss
+    g = make_assembly_graph("chr19", seed=5, genome_len=1_000_000)
+    src, dst, e, pe, y = _graph_tensors(g)
+    graph = gg.AssemblyGraph(src, dst, g.num_nodes)
+    torch.manual_seed(0)
+    model = gg.GraphGatedGCNModel(1, 2, 128, 16, 2, 64, True, 16).to(dev)
+    for per_op in (False, True):
+        model.per_op_path = per_op
+        model.zero_grad(set_to_none=True)
+        bce_loss(model(graph, None, e.to(dev), pe.to(dev)), y.to(dev), 1 / 16.5).backward()
+        arena = model._gg_last_arena
+        base = arena.tensor().data_ptr()
+        for p, off in arena.layout.entries:
+            assert p.grad.data_ptr() == base + 4 * off, "a gradient was copied out of the arena"
+        first = {k: p.grad.clone() for k, p in model.named_parameters()}
+        kept = {k: p.grad for k, p in model.named_parameters()}
+        model.zero_grad(set_to_none=True)
+        bce_loss(model(graph, None, (2 * e).to(dev), pe.to(dev)), y.to(dev), 1 / 16.5).backward()
+        assert model._gg_last_arena is not arena
+        for k in first:
+            assert torch.equal(first[k], kept[k])

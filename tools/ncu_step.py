@@ -30,7 +30,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
 def step():
     loss = crit(model(graph, None, e, pe).squeeze(-1), y)
-    opt.zero_grad(set_to_none=False)
+    opt.zero_grad(set_to_none=True)
     loss.backward()
     opt.step()
     return loss
