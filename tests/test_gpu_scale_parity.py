@@ -242,7 +242,9 @@ def test_one_call_model_path_equals_per_op_path(d, L, bn):
     r = oracle(src, dst, g.num_nodes, e, pe)
     bce_loss(r, y, 1 / 16.5).backward()
     assert rel_err(outs[False][0], r) < TOL
-    assert grads_close(outs[False][1], {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5) == []
+    # (default-initialised model: every gradient is small, so the floor for the biases batch norm cancels — true gradient
+    # exactly 0, what comes out is rounding noise — is set a decade higher than in the tests on trained-scale weights)
+    assert grads_close(outs[False][1], {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-4) == []
 
 
 def test_gradients_live_in_the_arena_and_survive_a_second_pass():

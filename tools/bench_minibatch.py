@@ -18,7 +18,8 @@ from gnnome_assembly_b200 import _lib
 from gnnome_assembly_b200.minibatch import ClusterGCNSampler, DataLoader
 from gnnome_assembly_b200.synth import make_assembly_graph
 
-K = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+sys.argv = [a for a in sys.argv if not a.startswith('--')] + [a for a in sys.argv if a.startswith('--')]
+K = int(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith('--') else 64
 BS = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 D = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 L = int(sys.argv[4]) if len(sys.argv) > 4 else 8
@@ -90,6 +91,28 @@ def epoch():
 
 epoch()
 torch.cuda.synchronize()
+# where does a batch's time go?  (a) device time of the library's own kernels (event pair per launch), (b) host profile
+_lib.profile(True)
+epoch()
+torch.cuda.synchronize()
+_lib.profile(False)
+prof = _lib.profile_report()
+kern_ms = sum(v[1] for v in prof.values())
+kern_launches = sum(v[0] for v in prof.values())
+host_top = None
+if "--host-profile" in sys.argv:
+    import cProfile
+    import io
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    epoch()
+    torch.cuda.synchronize()
+    pr.disable()
+    buf = io.StringIO()
+    pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+    host_top = buf.getvalue()
+    sys.stderr.write(host_top)
 t0 = time.perf_counter()
 reps = 3
 for _ in range(reps):
@@ -103,5 +126,6 @@ print(json.dumps({
                 "wall_us": wall_us, "algorithmic_bytes": alg_bytes, "gbps": alg_bytes / dev_us / 1e3,
                 "host_builder_us_same_subgraph": host_us},
     "epoch": {"batches": len(loader), "edges_in_batches": edges, "wall_ms": t_epoch * 1e3,
-              "edges_per_s": edges / t_epoch, "ms_per_batch": t_epoch * 1e3 / len(loader), "last_loss": last},
+              "edges_per_s": edges / t_epoch, "ms_per_batch": t_epoch * 1e3 / len(loader), "last_loss": last,
+              "library_kernel_ms_per_batch": kern_ms / len(loader), "library_launches_per_batch": kern_launches / len(loader)},
 }))
