@@ -127,5 +127,7 @@ print(json.dumps({
                 "host_builder_us_same_subgraph": host_us},
     "epoch": {"batches": len(loader), "edges_in_batches": edges, "wall_ms": t_epoch * 1e3,
               "edges_per_s": edges / t_epoch, "ms_per_batch": t_epoch * 1e3 / len(loader), "last_loss": last,
-              "library_kernel_ms_per_batch": kern_ms / len(loader), "library_launches_per_batch": kern_launches / len(loader)},
+              "library_kernel_ms_per_batch": kern_ms / len(loader), "library_launches_per_batch": kern_launches / len(loader),
+              "kernels_us": {k: [v[0] / len(loader), round(v[1] / v[0] * 1e3, 1)] for k, v in
+                             sorted(prof.items(), key=lambda kv: -kv[1][1])}},
 }))
