@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgnnome_b200.so")
-SOURCES = ["gg_plan.cu", "gg_api.cu", "gg_prep.cu", "gg_subgraph.cu", "gg_decode.cu", "gg_edge_mlp.cu", "gg_model.cu"]
+SOURCES = ["gg_plan.cu", "gg_api.cu", "gg_prep.cu", "gg_subgraph.cu", "gg_decode.cu", "gg_edge_mlp.cu", "gg_model.cu", "gg_plan_device.cu"]
 LIBS = ["-lcudart"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

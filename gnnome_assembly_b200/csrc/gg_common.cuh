@@ -70,6 +70,15 @@ struct Plan {
   void* sub_scratch = nullptr;    // SubScratch of a plan that has been used as a parent
 };
 
+// gg_plan_device.cu: the whole-graph plan built on the device (src / dst: device int32[E], caller edge order)
+int plan_create_device(const int32_t* src, const int32_t* dst, int64_t N, int64_t E, int flags, cudaStream_t st, Plan** out);
+
+#define GG_TRY_RC(call)       \
+  do {                        \
+    int _rc = (call);         \
+    if (_rc) return _rc;      \
+  } while (0)
+
 struct SubScratch;
 void free_sub_scratch(SubScratch* s);
 

@@ -133,6 +133,30 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
   GG_REQUIRE(N >= 0 && E >= 0, "plan_create: negative size");
   GG_REQUIRE(N < (1LL << 31) && E < (1LL << 31), "plan_create: int32 indices only");
   GG_REQUIRE(E == 0 || (src && dst), "plan_create: null edge list");
+  // Device builder (gg_plan_device.cu): sorts and relabelling on the GPU, one synchronisation.  A host-resident edge
+  // list is uploaded first (one H2D, E x 8 bytes).  GG_PLAN_HOST=1 selects the round-1 host builder below (kept as
+  // the reference the device builder is tested against, and for A/B timing).
+  if (std::getenv("GG_PLAN_HOST") == nullptr && !(flags & GG_PLAN_HOST_BUILD)) {
+    const int32_t* dsrc = src;
+    const int32_t* ddst = dst;
+    int32_t* up = nullptr;
+    if (E > 0 && !gg::is_device_ptr(src)) {
+      GG_CUDA(cudaMallocAsync((void**)&up, 2 * (size_t)E * sizeof(int32_t), stream));
+      GG_CUDA(cudaMemcpyAsync(up, src, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+      GG_CUDA(cudaMemcpyAsync(up + E, dst, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+      dsrc = up; ddst = up + E;
+    }
+    Plan* pl = nullptr;
+    const int rc = gg::plan_create_device(dsrc, ddst, N, E, flags, stream, &pl);
+    if (up) {
+      // the upload came from caller memory that may be pageable and die at return: wait for the copy (the builder
+      // itself has synchronised once already, so this is free unless the graph is huge)
+      cudaFreeAsync(up, stream);
+    }
+    if (rc) return rc;
+    *out = reinterpret_cast<gg_plan_t*>(pl);
+    return GG_OK;
+  }
   const bool timing = std::getenv("GG_PLAN_TIMING") != nullptr;
   auto t_start = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {

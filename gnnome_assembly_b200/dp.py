@@ -73,18 +73,49 @@ class ArenaSync:
     arena views as .grad without a copy.  All of it can be captured into a CUDA graph (train_step.GraphedTrainStep).
     """
 
-    def __init__(self, model, group=None, overlap=True):
+    def __init__(self, model, group=None, overlap=True, bucket_layers=None):
+        """bucket_layers: how many finished layer segments are reduced by one collective (1 = every layer on its own,
+        the default is read from GG_DP_BUCKET_LAYERS, else 4; 0 / overlap=False = ONE all-reduce of the whole arena in
+        finish()).  Each collective costs ~20 us of latency and borrows SMs from the persistent one-CTA-per-SM GEMMs
+        it overlaps with, so fewer, larger buckets win on small models."""
+        import os
         self.model, self.group, self.overlap = model, group, overlap
+        if bucket_layers is None:
+            bucket_layers = int(os.environ.get("GG_DP_BUCKET_LAYERS", "4"))
+        self.bucket_layers = int(bucket_layers) if overlap else 0
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.n_active = self.world
-        self._arena, self._pending, self._comm = None, [], None
+        self._arena, self._comm, self._buckets, self._next, self._done = None, None, [], 0, set()
         model.arena_hook = self._attach
 
     # ---- plumbing
     def _attach(self, arena):
         self._arena = arena
-        self._pending = [name for name, _, _ in arena.layout.segments]
-        arena.on_segment_ready = self._segment_ready
+        self._done = set()
+        self._next = 0
+        self._buckets = self._schedule(arena.layout)
+        arena.on_segment_ready = self._segment_ready if self.bucket_layers > 0 else None
+
+    def _schedule(self, layout):
+        """The collectives of one step, identical on every rank whatever its backward does: layer segments from the
+        last layer down in groups of `bucket_layers`; the final bucket takes the remaining layers and the head."""
+        segs = {name: (off, size) for name, off, size in layout.segments}
+        convs = sorted((n for n in segs if n.startswith("conv")), key=lambda n: -int(n[4:]))
+        groups, k = [], self.bucket_layers
+        if k > 0:
+            while len(convs) > k:
+                groups.append(convs[:k])
+                convs = convs[k:]
+        groups.append(convs + [n for n in segs if not n.startswith("conv")])
+        out = []
+        for names in groups:
+            lo = min(segs[n][0] for n in names)
+            hi = max(segs[n][0] + segs[n][1] for n in names)
+            if sum(segs[n][1] for n in names) == hi - lo:               # adjacent in the arena: one range
+                out.append([(lo, hi - lo)] + [names])
+            else:
+                out.append([segs[n] for n in names] + [names])
+        return out
 
     def _side_stream(self, dev):
         if dev.type != "cuda" or not self.overlap:
@@ -99,23 +130,25 @@ class ArenaSync:
         if self.n_active != 1:
             buf.mul_(1.0 / float(self.n_active))
 
-    def _segment(self, off, size, name):
+    def _issue(self, bucket):
         arena = self._arena
-        buf = arena.tensor()[off:off + size]
-        comm = self._side_stream(buf.device)
-        if comm is None:
-            self._reduce(buf)
-        else:
-            comm.wait_stream(torch.cuda.current_stream(buf.device))
-            with torch.cuda.stream(comm):
+        for off, size in bucket[:-1]:
+            buf = arena.tensor()[off:off + size]
+            comm = self._side_stream(buf.device)
+            if comm is None:
                 self._reduce(buf)
-        if name in self._pending:
-            self._pending.remove(name)
+            else:
+                comm.wait_stream(torch.cuda.current_stream(buf.device))
+                with torch.cuda.stream(comm):
+                    self._reduce(buf)
 
     def _segment_ready(self, off, size):
         for name, o, s in self._arena.layout.segments:
             if o == off and s == size:
-                self._segment(off, size, name)
+                self._done.add(name)
+        while self._next < len(self._buckets) - 1 and all(n in self._done for n in self._buckets[self._next][-1]):
+            self._issue(self._buckets[self._next])                          # (the last bucket waits for finish())
+            self._next += 1
 
     # ---- API
     def begin(self, n_active=None):
@@ -128,10 +161,9 @@ class ArenaSync:
         arena = self._arena
         if arena is None:
             raise RuntimeError("ArenaSync.finish: no forward pass has been run through the model")
-        seg = {name: (off, size) for name, off, size in arena.layout.segments}
-        order = [n for n in reversed(list(seg)) if n != "head"] + [n for n in seg if n == "head"]
-        for name in [n for n in order if n in self._pending]:                    # conv L-1 ... conv 0, head last
-            self._segment(*seg[name], name)
+        while self._next < len(self._buckets):                                   # what the backward has not issued yet
+            self._issue(self._buckets[self._next])
+            self._next += 1
         buf = arena.tensor()
         comm = self._side_stream(buf.device)
         if comm is not None:

@@ -22,7 +22,7 @@ _SUBPLAN_LOCK = threading.Lock()
 class GraphPlan:
     """Device-side CSR over in-edges (= internal edge order), CSR over out-edges, permutations."""
 
-    def __init__(self, src, dst, num_nodes, device=None, relabel=True):
+    def __init__(self, src, dst, num_nodes, device=None, relabel=True, host_build=False):
         src = torch.as_tensor(src)
         dst = torch.as_tensor(dst)
         if device is None:
@@ -41,7 +41,7 @@ class GraphPlan:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             rc = lib.gg_plan_create_ex(src32.data_ptr(), dst32.data_ptr(), self.num_nodes, self.num_edges,
-                                       1 if relabel else 0, stream, C.byref(handle))
+                                       (1 if relabel else 0) | (2 if host_build else 0), stream, C.byref(handle))
         _lib.check(rc, "gg_plan_create_ex")
         self.relabel = bool(relabel)
         self._handle = handle

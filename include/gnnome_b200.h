@@ -58,9 +58,10 @@ int gg_profile_report(char* buf, size_t cap);
  * Replaces the structure side of the DGLGraph argument of GraphGatedGCNModel.forward
  * (models/full_graph.py:22) and dgl.reverse (layers/gated_gcn_full.py:115).
  * src/dst: int32[E] in the caller's edge-id order, HOST or DEVICE memory.  Builds the internal edge order
- * (stable sort by dst = CSR over in-edges) and a CSR over out-edges that points into it, once per graph, on
- * the host (counting sort + breadth-first relabelling, ~27 ms for a chr19 graph) and uploads the arrays as one
- * library-owned device allocation; synchronises `stream`.  Internal position p holds caller edge perm[p].
+ * (stable sort by dst = CSR over in-edges) and a CSR over out-edges that points into it, once per graph, ON THE
+ * DEVICE (radix sorts + a two-level locality relabelling of the nodes, csrc/gg_plan_device.cu) into one
+ * library-owned device allocation; synchronises `stream` once (index check).  Internal position p holds caller
+ * edge perm[p].
  * (Per-batch sub-graph plans are built on the device: gg_subplan_* below.) */
 int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
                    void* stream, gg_plan_t** out);
@@ -68,6 +69,11 @@ int gg_plan_create(const int32_t* src, const int32_t* dst, int64_t num_nodes, in
  * neighbours of a node are close in memory (assembly graphs are near-linear, read ids are arbitrary).
  * Node features then live in INTERNAL node order: row p of h holds caller node node_perm[p]. */
 #define GG_PLAN_RELABEL 1
+/* GG_PLAN_HOST_BUILD: build on the host (the round-1 builder: D2H of the edge list, counting sort, exact breadth-first
+ * relabelling on one core, one upload) instead of on the device; also selected by the environment variable
+ * GG_PLAN_HOST=1.  Same arrays except for the node order under GG_PLAN_RELABEL (both are locality orders; the
+ * device one is a two-level region order, see csrc/gg_plan_device.cu). */
+#define GG_PLAN_HOST_BUILD 2
 int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges, int flags,
                       void* stream, gg_plan_t** out);
 int gg_plan_destroy(gg_plan_t* plan);

@@ -175,8 +175,9 @@ def _arena_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
     model = gg.GraphGatedGCNModel(1, 2, 64, 16, 2, 64, True, 16)          # host-resident: only the sync logic runs
-    sync = ArenaSync(model)
+    sync = ArenaSync(model, bucket_layers=1)          # conv1 | conv0 + head: two collectives per step
     layout = ensure_flat(model)
+    assert [b[-1] for b in sync._schedule(layout)] == [["conv1"], ["conv0", "head"]]
 
     def fake_backward(value):
         """what a backward pass does to the arena: fill, hand autograd-style views to .grad, signal the layers"""

@@ -5,7 +5,7 @@
 name=$1; flags=$2
 cd "$(dirname "$0")/../gnnome_assembly_b200/csrc" || exit 1
 objs=""
-for f in gg_plan gg_api gg_prep gg_subgraph gg_decode gg_edge_mlp gg_model; do
+for f in gg_plan gg_api gg_prep gg_subgraph gg_decode gg_edge_mlp gg_model gg_plan_device; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DGG_BUILD $flags -c $f.cu -o /tmp/ab_${name}_$f.o &
   objs="$objs /tmp/ab_${name}_$f.o"
 done

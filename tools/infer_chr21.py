@@ -45,12 +45,16 @@ g = g.to(dev)
 ol = torch.from_numpy(np.trunc(gs.overlap_length)).to(dev)
 sim = torch.from_numpy(gs.overlap_similarity).to(dev)
 y = torch.from_numpy(gs.y).to(dev)
-plan, t_plan = timed(lambda: gg.plan_for(g, dev))
+# lazy initialisation (CUDA module load, cub temp sizing, allocator) is paid on a toy graph, not on the timed one
+gg.GraphPlan(torch.tensor([0, 1, 2]), torch.tensor([1, 2, 0]), 3, dev)
+_, t_plan_host = timed(lambda: gg.GraphPlan(g.edges()[0], g.edges()[1], N, dev, host_build=True))     # round-1 builder
+plan, t_plan = timed(lambda: gg.plan_for(g, dev))                                                     # device builder
 e, t_feat = timed(lambda: prep.preprocess_features(ol, sim))                       # utils.py:67-75
 pe, t_pe = timed(lambda: prep.positional_encoding(g, 16))                          # utils.py:97-138 + train.py:249-251
 with torch.no_grad():
     model(g, None, e, pe)                                                          # warm-up (lazy init, allocator)
     scores, t_fwd = timed(lambda: model(g, None, e, pe))                           # inference.py:335
+    prep.bce_with_logits_and_metrics(scores, y, 1.0)                               # warm-up (first call: module load)
     (loss, tfpn), t_met = timed(lambda: prep.bce_with_logits_and_metrics(scores, y, 1.0))
 tp, tn, fp, fn = (float(x) for x in tfpn.tolist())
 g.edata["score"] = scores.squeeze(-1)
@@ -69,7 +73,7 @@ if "--check" in sys.argv:
     err = rel_err(scores.cpu(), ref)
 print(json.dumps({
     "workload": f"configs[2]: chr21-like synthetic graph N={N} E={E}, {weights} (L=16 d=256), inference.py:324-369",
-    "ms": {"plan_host": t_plan, "zscore_features": t_feat, "positional_encoding": t_pe, "forward": t_fwd,
+    "ms": {"plan_device": t_plan, "plan_host_builder": t_plan_host, "zscore_features": t_feat, "positional_encoding": t_pe, "forward": t_fwd,
            "loss_and_metrics": t_met, "decode_get_contigs": t_dec},
     "forward_edges_per_s": E / t_fwd * 1e3,
     "metrics": {"TP": tp, "TN": tn, "FP": fp, "FN": fn, "acc": (tp + tn) / max(tp + tn + fp + fn, 1)},
