@@ -141,7 +141,7 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
     const int32_t* ddst = dst;
     int32_t* up = nullptr;
     if (E > 0 && !gg::is_device_ptr(src)) {
-      GG_CUDA(cudaMallocAsync((void**)&up, 2 * (size_t)E * sizeof(int32_t), stream));
+      GG_CUDA(cudaMalloc((void**)&up, 2 * (size_t)E * sizeof(int32_t)));
       GG_CUDA(cudaMemcpyAsync(up, src, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
       GG_CUDA(cudaMemcpyAsync(up + E, dst, E * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
       dsrc = up; ddst = up + E;
@@ -149,9 +149,8 @@ int gg_plan_create_ex(const int32_t* src, const int32_t* dst, int64_t N, int64_t
     Plan* pl = nullptr;
     const int rc = gg::plan_create_device(dsrc, ddst, N, E, flags, stream, &pl);
     if (up) {
-      // the upload came from caller memory that may be pageable and die at return: wait for the copy (the builder
-      // itself has synchronised once already, so this is free unless the graph is huge)
-      cudaFreeAsync(up, stream);
+      cudaStreamSynchronize(stream);        // host-resident edge list only: the staging copy is released synchronously
+      cudaFree(up);
     }
     if (rc) return rc;
     *out = reinterpret_cast<gg_plan_t*>(pl);

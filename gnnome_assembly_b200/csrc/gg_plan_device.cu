@@ -11,7 +11,7 @@
 // Node relabelling (GG_PLAN_RELABEL).  Goal: neighbours close in memory (assembly graphs are near-linear, read ids are
 // arbitrary).  A level-synchronous breadth-first search is hopeless here: the graph's diameter is thousands of levels.
 // Two-level ordering instead, all data-parallel except one warp:
-//   1. REGIONS: every 64th node id seeds a region; (distance, seed) keys are relaxed over the edges with 64-bit
+//   1. REGIONS: one node in 64 (by a hash of its id) seeds a region; (distance, seed) keys are relaxed over the edges with 64-bit
 //      atomicMin until nothing changes (a cooperative kernel, grid sync per sweep; ~10 sweeps: a region's radius).  The
 //      fixed point — nearest seed, ties to the smaller seed id — does not depend on execution order.  Components that
 //      hold no seed are re-seeded (every 4th remaining node, then every remaining node).
@@ -23,6 +23,8 @@
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "gg_common.cuh"
@@ -32,7 +34,6 @@ namespace cg = cooperative_groups;
 namespace gg {
 
 constexpr unsigned long long kInfKey = ~0ull;
-constexpr int kSeedStride = 64;
 
 __global__ void plan_check_degree_kernel(int64_t E, int64_t N, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                          int32_t* __restrict__ udeg, int* __restrict__ err) {
@@ -54,11 +55,14 @@ __global__ void __launch_bounds__(256) plan_regions_kernel(int64_t E, int64_t N,
   for (int round = 0; round < 3; ++round) {
     for (int64_t v = tid; v < N; v += nth) {
       const bool connected = udeg[v] > 0;
+      // seeds are drawn by a multiplicative hash of the id, NOT by id modulo: assembly graphs put the two strands of
+      // read k at ids 2k / 2k+1 and the strands are separate components, so "every 64th id" seeds one strand only
+      const unsigned hv = (unsigned)v * 2654435761u;
       if (round == 0) {
-        const bool seed = connected && (v % kSeedStride == 0);
+        const bool seed = connected && (hv >> 26) == 0;             // 1 in 64
         key[v] = seed ? (unsigned long long)v : kInfKey;
         is_seed[v] = seed ? 1 : 0;
-      } else if (connected && key[v] == kInfKey && (round == 2 || v % 4 == 0)) {
+      } else if (connected && key[v] == kInfKey && (round == 2 || ((hv >> 8) & 3u) == 0)) {
         key[v] = (unsigned long long)v;
         is_seed[v] = 1;
       }
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256) plan_regions_kernel(int64_t E, int64_t N,
         if (kd != kInfKey && kd + (1ull << 32) < ks) { atomicMin(key + s, kd + (1ull << 32)); any = 1; }
       }
       if (any) changed[sweep & 1] = 1;
+      if (tid == 0) atomicAdd(changed + 2, 1);              // sweep counter (diagnostics)
       grid.sync();
       if (!changed[sweep & 1]) break;
       grid.sync();                                           // (the flag of this parity is reset two sweeps later)
@@ -226,14 +231,38 @@ static int bits_for(int64_t n) {
   return b;
 }
 
-struct TempPool {                      // stream-ordered scratch, released when the builder returns
+// Stream-ordered scratch from a memory pool of the library's own (one per device) that keeps up to 1 GiB cached between
+// calls: with the default pool every synchronisation hands the memory back to the driver, and the ~25 scratch arrays of
+// one build then cost ~8 ms of allocation calls — more than all the kernels together.
+static cudaMemPool_t scratch_pool() {
+  static cudaMemPool_t pools[kMaxDevices] = {};
+  const int dev = current_device();
+  if (pools[dev] == nullptr) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    unsigned long long keep = 1ull << 30;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = pool;
+  }
+  return pools[dev];
+}
+
+struct TempPool {                      // released (back to the pool) when the builder returns
   cudaStream_t st;
+  cudaMemPool_t pool;
   std::vector<void*> ptrs;
-  explicit TempPool(cudaStream_t s) : st(s) {}
+  explicit TempPool(cudaStream_t s) : st(s), pool(scratch_pool()) {}
   ~TempPool() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   template <class T> T* get(size_t n) {
     void* p = nullptr;
-    if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st) != cudaSuccess) return nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    const cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, bytes, pool, st) : cudaMallocAsync(&p, bytes, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
     ptrs.push_back(p);
     return reinterpret_cast<T*>(p);
   }
@@ -374,6 +403,14 @@ int plan_create_device(const int32_t* src, const int32_t* dst, int64_t N, int64_
     GG_KERNEL_BEGIN("plan_region_bfs_kernel", st);
     plan_region_bfs_kernel<<<1, 32, 0, st>>>(seed_rank + N, rptr, radj, rqueue, rrank);
     GG_KERNEL_END("plan_region_bfs_kernel", st);
+    if (std::getenv("GG_PLAN_DEBUG")) {          // diagnostics (synchronises): region / region-edge counts, relaxation sweeps
+      int h[3] = {0, 0, 0};
+      cudaMemcpyAsync(&h[0], seed_rank + N, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&h[1], ppos + 2 * E, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&h[2], err + 3, sizeof(int), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      std::fprintf(stderr, "gg_plan_device: N=%lld E=%lld regions=%d region_edges=%d sweeps=%d\n", (long long)N, (long long)E, h[0], h[1], h[2]);
+    }
     GG_PLAN_LAUNCH("plan_node_keys_kernel", plan_node_keys_kernel, N, N, udeg, key, seed_rank, rrank, nkey, ids);
     GG_TRY_RC(sort_pairs(tp, nkey, nkey_sorted, ids, pl->node_perm, N, 48, st));
     GG_PLAN_LAUNCH("plan_invert_kernel", plan_invert_kernel, N, N, pl->node_perm, pl->node_inv);
