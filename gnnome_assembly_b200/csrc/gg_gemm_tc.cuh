@@ -98,11 +98,12 @@ enum TraceSlot { TR_PROD_WAIT_EMPTY = 0, TR_PROD_TOTAL, TR_MMA_WAIT_AB, TR_MMA_W
 __device__ unsigned long long gg_tc_trace[TR_SLOTS];      // this header is compiled into exactly one translation unit (gg_api.cu)
 struct Tracer {
   unsigned long long t0 = 0, t_role = 0;
-  __device__ __forceinline__ void role_begin() { if constexpr (kTrace) t_role = clock64(); }
-  __device__ __forceinline__ void role_end(int slot) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], clock64() - t_role); }
-  __device__ __forceinline__ void begin() { if constexpr (kTrace) t0 = clock64(); }
-  __device__ __forceinline__ void end(int slot) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], clock64() - t0); }
-  __device__ __forceinline__ void count(int slot, unsigned long long n) { if constexpr (kTrace) atomicAdd(&gg_tc_trace[slot], n); }
+  bool on = true;      // runtime filter (gg_debug_flags bit 4: kernels with an A transform only; bit 5: edge-gate epilogue only)
+  __device__ __forceinline__ void role_begin() { if constexpr (kTrace) if (on) t_role = clock64(); }
+  __device__ __forceinline__ void role_end(int slot) { if constexpr (kTrace) if (on) atomicAdd(&gg_tc_trace[slot], clock64() - t_role); }
+  __device__ __forceinline__ void begin() { if constexpr (kTrace) if (on) t0 = clock64(); }
+  __device__ __forceinline__ void end(int slot) { if constexpr (kTrace) if (on) atomicAdd(&gg_tc_trace[slot], clock64() - t0); }
+  __device__ __forceinline__ void count(int slot, unsigned long long n) { if constexpr (kTrace) if (on) atomicAdd(&gg_tc_trace[slot], n); }
 };
 
 struct Args {
@@ -266,7 +267,7 @@ struct BnBwdATx {
 template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx, bool kWRes = false>
 __global__ void __launch_bounds__(threads<ATx>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, Args g, Epi epi, ATx atx) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmOut2, Args g, Epi epi, ATx atx) {
   static_assert(!ATx::kActive || !A_MN, "A transforms are written for K-major A");
   constexpr int kStages = Cfg<ATx, Epi, kWRes>::kStages;
   constexpr int kStageBytes = Cfg<ATx, Epi, kWRes>::kStageBytes;
@@ -297,6 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tmem_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
   auto tmem_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
   const uint32_t bres_full = bars + 8u * 17, bres_ready = bars + 8u * 18;     // W-resident B: loaded / split
+  auto gt_full = [&](int s) { return bars + 8u * (19 + s); };                   // A transform: g_t tile of stage s is in smem
   const uint32_t bres0 = stage0 + kStages * kStageBytes;                         // B_hi K-blocks, then B_lo K-blocks
   const int nkb_total = (int)((g.K + BK - 1) / BK);                              // kWRes: <= 4
 
@@ -310,9 +312,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 "setmaxnreg split exceeds the CTA's register pool: setmaxnreg.inc would block forever");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
+  const bool trace_this = kTrace && (!(g.dbg & 16) || ATx::kActive) && (!(g.dbg & 32) || (Epi::kIdx && !Epi::kRowReduce));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_raw(s), 1); mbar_init(full_ab(s), kConvThreads); mbar_init(empty(s), 1); }
+    // a stage is free when its MMAs have completed AND (A transform) the bulk store of its g_t tile has read shared memory
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_raw(s), 1); mbar_init(full_ab(s), kConvThreads); mbar_init(empty(s), ATx::kActive ? 2 : 1);
+      if constexpr (ATx::kActive) mbar_init(gt_full(s), kConvThreads);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 256); }
     if constexpr (kWRes) { mbar_init(bres_full, 1); mbar_init(bres_ready, kConvThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -384,6 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ================================================================ TMA producer
       int s = 0; uint32_t ph = 0;
       Tracer tr;
+      tr.on = trace_this;
       tr.role_begin();
       tr.count(TR_CTAS, 1);
       if constexpr (kWRes) {
@@ -434,6 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(false, B_MN);          // A comes from TMEM: always K-major there
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
       Tracer tr;
+      tr.on = trace_this;
       tr.role_begin();
       if constexpr (kWRes) {
         if (blockIdx.x < total_work) { mbar_wait(bres_ready, 0u); tc_fence_after(); }
@@ -470,6 +479,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
       tr.role_end(TR_MMA_TOTAL);
+    } else if (ATx::kActive && warp == 3 && lane == 0) {
+      // ================================================================ g_t store (A transform only)
+      // The converter threads own one A row each, so a direct global store of g_t is 32 scattered 16-byte pieces per
+      // warp instruction (32 LSU wavefronts per 512 bytes: the single largest item on the kernel's busiest pipe).  They
+      // write g_t back into the stage's `t` slot instead (same swizzled positions they just read), and this thread
+      // sends the finished 128 x 32 tile to global memory with ONE bulk tensor store; the stage is released to the
+      // producer when the store has finished reading shared memory.
+      if constexpr (ATx::kActive) {
+        int s = 0; uint32_t ph = 0;
+        for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+          int mt, nt, sp; decode(w, mt, nt, sp);
+          int64_t kbeg; int nkb; k_range(sp, kbeg, nkb);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(gt_full(s), ph);
+            if (nt == 0) {
+              const uint32_t st = stage0 + s * kStageBytes + kOffA2;
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmOut2), "r"(st), "r"((int)(kbeg + (int64_t)kb * BK)), "r"(mt * BM) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            mbar_arrive(empty(s));
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+          }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // the stores have landed before the CTA exits
+      }
     }
   } else if (ATx::kActive && warp < kEpiWarp0) {
     // ================================================================ converter with an A transform
@@ -483,6 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t lane_base = (uint32_t)(32 * (cw & 3)) << 16;
       int s = 0; uint32_t ph = 0;
       Tracer tr;
+      tr.on = trace_this;
       const bool tr_on = kTrace && ct == 0;
       if (tr_on) tr.role_begin();
       if constexpr (kWRes) split_resident_b(ct);
@@ -497,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint8_t* st = gen + s * kStageBytes;
           // g_eo[row, c0 + 16 half ..+15] (tile 0) and t (tile 3) -> g_t (stored, and the A operand)
           const float4* row = reinterpret_cast<const float4*>(st + t * 128);
-          const float4* row2 = reinterpret_cast<const float4*>(st + kOffA2 + t * 128);
+          float4* row2 = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + kOffA2 + t * 128);
           const int c0 = (int)(kbeg + (int64_t)kb * BK);
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -517,8 +554,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               gt[j] = fmaf(cb.x, gn, -cb.y) - xh * cb.z;
               hi[4 * c + j] = __float_as_uint(gt[j]);
             }
-            if (nt == 0 && m < g.M)
-              *reinterpret_cast<float4*>(atx.g_t + m * atx.ld + c0 + 4 * cc) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+            // g_t replaces t in the stage (this thread's own 16-byte chunk): stored by the bulk-store thread
+            row2[cc ^ (t & 7)] = make_float4(gt[0], gt[1], gt[2], gt[3]);
           }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -545,8 +582,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tmem_st_wait();
           tc_fence_before();
-          proxy_fence_async();
+          proxy_fence_async();                           // generic-proxy smem writes (g_t, B_lo) -> async proxy (MMA, bulk store)
           mbar_arrive(full_ab(s));
+          mbar_arrive(gt_full(s));
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
@@ -559,6 +597,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     int s = 0; uint32_t ph = 0;
     Tracer tr;
+    tr.on = trace_this;
     const bool tr_on = kTrace && t == 0;
     if (tr_on) tr.role_begin();
     if constexpr (kWRes) split_resident_b(t);
@@ -691,6 +730,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
 
     Tracer tr;
+    tr.on = trace_this;
     const bool tr_on = kTrace && tg == 0 && grp == 0;
     if (tr_on) tr.role_begin();
     int acc = 0; uint32_t acc_ph = 0;
@@ -879,12 +919,20 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   if (rc) return rc;
   if (B_MN) rc = make_map(&tmB, B, N, K, ldb, 32, true); else rc = make_map(&tmB, B, K, N, ldb, BN, false);
   if (rc) return rc;
-  if (ATx::kActive) {
+  CUtensorMap tmOut2;
+  if constexpr (ATx::kActive) {
     if (K > 256) { set_error("gnnome_b200: A transform supports K <= 256"); return GG_ERR_UNSUPPORTED; }
     rc = make_map(&tmA2, A2, K, M, lda, BM, false);
     if (rc) return rc;
+    if (atx.ld % 4 != 0 || reinterpret_cast<uintptr_t>(atx.g_t) % 16 != 0) {
+      set_error("gnnome_b200: g_t must be 16-byte aligned with a leading dimension that is a multiple of 4");
+      return GG_ERR_ARG;
+    }
+    rc = make_map(&tmOut2, atx.g_t, K, M, atx.ld, BM, false);       // same geometry as the t tiles it replaces in the stage
+    if (rc) return rc;
   } else {
     tmA2 = tmA;
+    tmOut2 = tmA;
   }
   Args g{};
   g.M = M; g.N = N; g.K = K;
@@ -914,7 +962,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
     attr_set = true;
   }
   GG_KERNEL_BEGIN(tag, st);
-  kern<<<grid, threads<ATx>(), kSmem, st>>>(tmA, tmB, tmA2, g, epi, atx);
+  kern<<<grid, threads<ATx>(), kSmem, st>>>(tmA, tmB, tmA2, tmOut2, g, epi, atx);
   GG_KERNEL_END(tag, st);
   return GG_OK;
 }

@@ -80,3 +80,14 @@ ho, eo = layer.forward_internal(plan, h, e)
 read()
 torch.autograd.backward([ho, eo], [ho, eo])
 report("layer backward (g_e_in GEMM with the A transform, dB3, g_h_in, dWn)", read())
+# isolate single kernels with the runtime filter (gg_debug_flags bit 4 / bit 5)
+lib.gg_debug_flags(32)
+with torch.no_grad():
+    layer.forward_internal(plan, h, e)
+report("edge-gate GEMM alone (EpiEdgeGate)", read())
+lib.gg_debug_flags(16)
+ho, eo = layer.forward_internal(plan, h, e)
+read()
+torch.autograd.backward([ho, eo], [ho, eo])
+report("g_e_in GEMM alone (BnBwdATx)", read())
+lib.gg_debug_flags(0)
