@@ -247,6 +247,7 @@ struct EpiBias {
   float* C; int64_t ldc; const float* bias; int relu;
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = true;      // tensor-core kernel: 64-column staging tile, 3 stages
+  static constexpr bool kMidStaging = false;
   static constexpr bool kRowReduce = false;
   struct PreD {};
   struct PreN {};
@@ -289,6 +290,11 @@ struct EpiAddMaskT {
   }
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = false;
+#ifdef GG_MID_ADD       // A/B builds: 32-column chunks (whole lines per row piece) + 3 stages for the bwd-data GEMMs
+  static constexpr bool kMidStaging = true;
+#else
+  static constexpr bool kMidStaging = false;
+#endif
   static constexpr bool kRowReduce = false;
   struct Empty {};
   struct Val { float4 v; };
@@ -316,6 +322,7 @@ struct EpiAtomic {
   float* C; int64_t ldc;
   static constexpr bool kIdx = false;
   static constexpr bool kWideStaging = false;
+  static constexpr bool kMidStaging = false;
   static constexpr bool kRowReduce = false;
   struct PreD {};
   struct PreN {};
@@ -337,8 +344,9 @@ struct EpiAtomic {
 struct EpiEdgeGate {
   float* t; int d; const float* b3; const float* P; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
-  static constexpr bool kWideStaging = false;     // d = 128 runs W-resident (16-column chunks); at d = 256 the wide tile
-                                                  // measured 3-4 % slower on the 1M-edge graph (same-box A/B, tools/ab_sweep.sh)
+  static constexpr bool kWideStaging = false;     // (the 64-column tile does not fit next to the resident W at d = 128 and
+                                                  // measured 3-4 % slower at d = 256, same-box A/B, tools/ab_sweep.sh)
+  static constexpr bool kMidStaging = true;       // 32-column chunks: every gathered / stored row piece is a whole line
   static constexpr bool kRowReduce = false;
   struct PreD { float4 p1; };     // B1h[src]: random row gather -> a whole tile ahead
   struct PreN { float4 p2; };     // B2h[dst]: edges are dst-sorted, consecutive rows share it -> one chunk ahead
@@ -409,6 +417,7 @@ struct EpiScoreTC {
   float* score; float* hid; const float* Q; const float* w2; const float* b2; const int32_t* src; const int32_t* dst;
   static constexpr bool kIdx = true;
   static constexpr bool kWideStaging = true;
+  static constexpr bool kMidStaging = false;
   static constexpr bool kRowReduce = true;
   static constexpr int H = 64;
   struct PreD { float4 q1; };     // Q[src, n]

@@ -61,13 +61,22 @@ struct Cfg {
   // is loaded and split ONCE per CTA; the ring then carries only A tiles.  The kernel is bound by the LSU /
   // shared-memory pipe (ncu: l1tex 66-70 % busy, everything else < 40 %), and per K-block the B side was 16 KB of
   // TMA writes + 32 KB of split traffic out of ~128 KB.
-  static constexpr int kStages = kWRes ? (ATx::kActive ? 2 : 4) : ((ATx::kActive || kWide) ? 3 : 4);
+  // mid staging (fused gather epilogues: EpiEdgeGate): 32-column chunks, i.e. one whole 128-byte line per row and chunk.
+  // Per-role cycle traces (profiles/r2_tc_trace_d128.txt) show this kernel paced by its epilogue, and the epilogue by
+  // the LSU wavefront count: with 16-column chunks every gathered / stored row piece is HALF a line (64 bytes), so the
+  // 128 KB of B1h[src] / B2h[dst] gathers and the 64 KB of t stores of a tile cost twice the wavefronts they need.
+#ifdef GG_NO_MID
+  static constexpr bool kMid = false;
+#else
+  static constexpr bool kMid = !ATx::kActive && !kWide && Epi::kMidStaging;
+#endif
+  static constexpr int kStages = kWRes ? (ATx::kActive ? 2 : (kMid ? 3 : 4)) : ((ATx::kActive || kWide || kMid) ? 3 : 4);
   static constexpr int kATiles = ATx::kActive ? 2 : 1;
   static constexpr int kStageBytes = (kWRes ? kATiles : kATiles + 2) * TILE_BYTES;
   static constexpr int kOffA2 = kWRes ? TILE_BYTES : 3 * TILE_BYTES;        // second streamed A tile (A transform)
   static constexpr int kBResBytes = kWRes ? 8 * TILE_BYTES : 0;            // [4 K-blocks hi][4 K-blocks lo]
   static constexpr int kPipeBytes = kStages * kStageBytes + kBResBytes;
-  static constexpr int kEC = kWide ? 64 : 16;                     // epilogue chunk width in accumulator columns
+  static constexpr int kEC = kWide ? 64 : (kMid ? 32 : 16);       // epilogue chunk width in accumulator columns
   static constexpr int kStagingBytes = 2 * BM * kEC * 4;
 };
 template <bool kStats, class Epi, class ATx, bool kWRes = false>
