@@ -9,8 +9,9 @@ from gnnome_assembly_b200.synth import make_assembly_graph
 
 dev = torch.device("cuda:0")
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
-edges = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1000000", "5000000", "20000000"])]
-dims = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["64", "128", "256"])]
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+edges = [int(x) for x in (_pos[0].split(",") if len(_pos) > 0 else ["1000000", "5000000", "20000000"])]
+dims = [int(x) for x in (_pos[1].split(",") if len(_pos) > 1 else ["64", "128", "256"])]
 
 
 def timed(fn, n):
@@ -53,13 +54,22 @@ for E_target in edges:
             torch.cuda.synchronize()
             n = 7 if E * d < 2e9 else 3
             tf, tb = timed(fwd, n), timed(fwd_bwd, n)
+            kern = None
+            if "--kernels" in sys.argv:                       # per-kernel device time of one fwd+bwd (event pair per launch)
+                from gnnome_assembly_b200 import _lib
+                _lib.profile(True)
+                fwd_bwd()
+                torch.cuda.synchronize()
+                _lib.profile(False)
+                kern = {k: round(v[1] * 1e3 / v[0], 1) for k, v in sorted(_lib.profile_report().items(), key=lambda kv: -kv[1][1])}
             bf = 4 * d * (3 * E + 25 * N) + 16 * E
             bb = 4 * d * (11 * E + 67 * N) + 32 * E
             print(json.dumps({"E": E, "N": N, "d": d, "L": 1, "fwd_ms": tf * 1e3, "fwd_bwd_ms": tb * 1e3,
                               "fwd_edges_per_s": E / tf, "fwd_bwd_edges_per_s": E / tb,
                               "fwd_gbps": bf / tf / 1e9, "fwd_frac": bf / tf / 1e9 / peak,
                               "fwd_bwd_gbps": bb / tb / 1e9, "fwd_bwd_frac": bb / tb / 1e9 / peak,
-                              "graph_and_plan_s": t_plan, "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+                              "graph_and_plan_s": t_plan, "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                              **({"kernels_us": kern} if kern else {})}), flush=True)
         except torch.OutOfMemoryError as ex:
             print(json.dumps({"E": E, "N": N, "d": d, "error": "out of memory"}), flush=True)
         finally:
