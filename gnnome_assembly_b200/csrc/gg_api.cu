@@ -108,7 +108,9 @@ static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const flo
     // persistent CTAs, one work item (tile x split) at a time: the items must fit ONE wave.  Rounding the split count
     // up (5 tiles x 30 splits = 150 items on 148 SMs) made two CTAs run a second item while 146 idled: floor.
     int64_t want = sm_count() / tiles;
-    const int64_t max_by_k = (M + 1023) / 1024;
+    // at least 256 reduction rows (8 K-blocks) per split: a mini-batch sub-graph (20-40 k edges) then still spreads over
+    // ~100 CTAs instead of ~25 (each K-block is a TMA round trip: 32 of them in a row were 33 us for a 23 k-edge batch)
+    const int64_t max_by_k = (M + 255) / 256;
     if (want > max_by_k) want = max_by_k;
     if (want < 1) want = 1;
     return tc::launch<true, true, false, true>(tag, dY, lddy, X, ldx, N, K, M, (int)want, nullptr, db, epi, sm_count(), st);
