@@ -408,12 +408,13 @@ def run_ours(args):
         r = kernels[dom]
         # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (same workload)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic.json")
-        if os.path.exists(tpath):
+        tfile = next((f for f in ("r2_ncu_dram_traffic.json", "r1_ncu_dram_traffic.json")
+                      if os.path.exists(os.path.join(ROOT, "profiles", f))), None)
+        if tfile:
             key = {"gemm_edge_gate": "EpiEdgeGate", "gemm_bwd_e_in": "BnBwdATx", "gemm_dB3": "EpiAtomic"}.get(dom, dom)
-            for name, rec in json.load(open(tpath)).items():
+            for name, rec in json.load(open(os.path.join(ROOT, "profiles", tfile))).items():
                 if key in name and (E == 372650 and D == 128):
-                    traffic, traffic_src = rec["dram_bytes_per_launch"], "profiles/r1_ncu_dram_traffic.json (" + rec["report"] + ")"
+                    traffic, traffic_src = rec["dram_bytes_per_launch"], f"profiles/{tfile} (" + rec["report"] + ")"
                     break
         roofline = {"kernel": dom, "bound": "hbm", "achieved": r["gbps"], "peak": peak, "unit": "GB/s",
                     "frac": r["frac"], "traffic": traffic,
