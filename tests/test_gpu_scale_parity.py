@@ -238,7 +238,7 @@ def test_one_call_model_path_equals_per_op_path(d, L, bn):
             s_inf = model(graph, None, e.to(dev), pe.to(dev))              # inference layout of the workspace
         assert rel_err(s_inf, s) < 1e-6
     assert rel_err(outs[False][0], outs[True][0]) < 1e-6
-    assert grads_close(outs[False][1], outs[True][1], rtol=1e-5, atol_frac=1e-6) == []
+    assert grads_close(outs[False][1], outs[True][1], rtol=1e-4, atol_frac=1e-5) == []   # (split-K fp32 atomics: order varies run to run)
     r = oracle(src, dst, g.num_nodes, e, pe)
     bce_loss(r, y, 1 / 16.5).backward()
     assert rel_err(outs[False][0], r) < TOL
