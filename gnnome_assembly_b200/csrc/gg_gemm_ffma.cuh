@@ -253,8 +253,18 @@ struct EpiBias {
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
   __device__ __forceinline__ void prefetch_near(PreN&, int64_t, int, int, int) const {}
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, bool valid) const {
-    apply<4>(m, n, acc, valid);
+  struct ChunkC { float4 b; };     // the bias of this thread's four columns
+  __device__ __forceinline__ ChunkC chunk_const(int n, bool ok) const {
+    ChunkC c;
+    c.b = (ok && bias) ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, const ChunkC& c,
+                                            bool valid) const {
+    if (!valid) return;
+    acc[0] += c.b.x; acc[1] += c.b.y; acc[2] += c.b.z; acc[3] += c.b.w;
+    if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
+    *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
   template <int GW>
   __device__ __forceinline__ void apply(int64_t m, int n, float (&acc)[GW], bool valid) const {
@@ -306,7 +316,10 @@ struct EpiAddMaskT {
   __device__ __forceinline__ void prefetch_near(PreN& p, int64_t m, int n, int, int) const {
     if constexpr (kMask) p.v = __ldg(reinterpret_cast<const float4*>(mask + m * ldc + n));
   }
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, bool valid) const {
+  struct ChunkC {};
+  __device__ __forceinline__ ChunkC chunk_const(int, bool) const { return ChunkC{}; }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, const ChunkC&,
+                                            bool valid) const {
     if (!valid) return;
     if constexpr (kAdd) { acc[0] += d.v.x; acc[1] += d.v.y; acc[2] += d.v.z; acc[3] += d.v.w; }
     if constexpr (kMask) {
@@ -328,7 +341,10 @@ struct EpiAtomic {
   struct PreN {};
   __device__ __forceinline__ void prefetch_deep(PreD&, int64_t, int, int, int) const {}
   __device__ __forceinline__ void prefetch_near(PreN&, int64_t, int, int, int) const {}
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, bool valid) const {
+  struct ChunkC {};
+  __device__ __forceinline__ ChunkC chunk_const(int, bool) const { return ChunkC{}; }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD&, const PreN&, const ChunkC&,
+                                            bool valid) const {
     apply<4>(m, n, acc, valid);
   }
   template <int GW>
@@ -356,9 +372,16 @@ struct EpiEdgeGate {
   __device__ __forceinline__ void prefetch_near(PreN& p, int64_t, int n, int, int v) const {
     p.p2 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)v * (5 * d) + 4 * d + n));
   }
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& dp, const PreN& np, bool valid) const {
+  struct ChunkC { float4 b; };     // b3 of this thread's four columns
+  __device__ __forceinline__ ChunkC chunk_const(int n, bool ok) const {
+    ChunkC c;
+    c.b = ok ? __ldg(reinterpret_cast<const float4*>(b3 + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
+  }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& dp, const PreN& np, const ChunkC& c,
+                                            bool valid) const {
     if (!valid) return;
-    const float4 b = __ldg(reinterpret_cast<const float4*>(b3 + n));
+    const float4 b = c.b;
     acc[0] = (dp.p1.x + np.p2.x) + (acc[0] + b.x);
     acc[1] = (dp.p1.y + np.p2.y) + (acc[1] + b.y);
     acc[2] = (dp.p1.z + np.p2.z) + (acc[2] + b.z);
@@ -428,7 +451,10 @@ struct EpiScoreTC {
   __device__ __forceinline__ void prefetch_near(PreN& p, int64_t, int n, int, int v) const {
     if (n < H) p.q2 = __ldg(reinterpret_cast<const float4*>(Q + (int64_t)v * (2 * H) + H + n));
   }
-  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, bool valid) const {
+  struct ChunkC {};
+  __device__ __forceinline__ ChunkC chunk_const(int, bool) const { return ChunkC{}; }
+  __device__ __forceinline__ void apply_pre(int64_t m, int n, float (&acc)[4], const PreD& d, const PreN& p, const ChunkC&,
+                                            bool valid) const {
     if (!valid) { acc[0] = acc[1] = acc[2] = acc[3] = 0.f; return; }
     acc[0] = fmaxf(acc[0] + d.q1.x + p.q2.x, 0.f);
     acc[1] = fmaxf(acc[1] + d.q1.y + p.q2.y, 0.f);

@@ -228,6 +228,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load now, wait once for several of them.  The wait carries the destination registers as
+// read-write operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_fence(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), LBO [16,30),
 // SBO [32,46) (all >> 4), version = 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64)
 // K-major operands use SWIZZLE_128B (16-byte chunks permuted over 8 rows).  MN-major TF32 operands
@@ -745,6 +762,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_ph = 0;
     int cur = 0;                                        // idx buffer of the current tile
     int64_t w = blockIdx.x;
+    if (g.n_tiles == 1 && 64 * grp >= g.N) {
+      // N <= 64 (the score predictor's hidden layer): this group's 64 columns are never valid.  It only hands the
+      // accumulators back; its group barriers, staging and idx buffers are its own, so skipping them is consistent.
+      for (; w < total_work; w += gridDim.x) {
+        mbar_wait(tmem_full(acc), acc_ph);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(tmem_empty(acc));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
     int mt = 0, nt = 0, sp = 0, mtn = 0, ntn = 0, spn = 0;
     if (w < total_work) {
       decode(w, mt, nt, sp);
@@ -769,19 +797,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m0 = (int64_t)mt * BM;
 #pragma unroll
       for (int q = 0; q < QN; ++q) {
+        {
+          // all of the chunk's TMEM loads are issued before the first wait (one round trip instead of EC / 16)
+          uint32_t v[EC / 16][16];
 #pragma unroll
-        for (int sub = 0; sub < EC / 16; ++sub) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v);
-          if (q == QN - 1 && sub == EC / 16 - 1) {      // accumulator fully read: hand it back to the MMA warp
+          for (int sub = 0; sub < EC / 16; ++sub)
+            tmem_ld16_issue(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v[sub]);
+#pragma unroll
+          for (int sub = 0; sub < EC / 16; ++sub) tmem_ld16_fence(v[sub]);
+          if (q == QN - 1) {                            // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            stg[tg * TPR + ((4 * sub + j) ^ swz(tg))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int sub = 0; sub < EC / 16; ++sub)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stg[tg * TPR + ((4 * sub + j) ^ swz(tg))] =
+                  make_float4(__uint_as_float(v[sub][4 * j]), __uint_as_float(v[sub][4 * j + 1]),
+                              __uint_as_float(v[sub][4 * j + 2]), __uint_as_float(v[sub][4 * j + 3]));
         }
         group_bar();
+        // operands that depend on the column only (bias rows): once per chunk, not once per pass
+        const typename Epi::ChunkC cconst = epi.chunk_const(col_of(nt, q), col_of(nt, q) < g.N);
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int p = 0; p < PPC; ++p) {
@@ -791,7 +829,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int64_t m = m0 + r;
           const int n = col_of(nt, q);
           const bool valid = (m < g.M) && (n < g.N);
-          epi.apply_pre(m, n, a, deep[q][p], near[q][p], valid);
+          epi.apply_pre(m, n, a, deep[q][p], near[q][p], cconst, valid);
           if constexpr (Epi::kRowReduce) {
             // one scalar per output row: the TPR threads of the row are consecutive lanes (wide staging only)
             static_assert(!Epi::kRowReduce || EC == 64, "row reductions need the 64-column staging tile");

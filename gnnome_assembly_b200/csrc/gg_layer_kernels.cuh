@@ -381,8 +381,11 @@ node_bwd_apply_kernel(int64_t N, const float* __restrict__ z, const float* __res
 //   g_eo = g_e + g_sigma*sigma*(1-sigma)            -> stored
 //   g_n  = g_eo*[n>0];  bstats_e += [g_n | g_n*xhat_e]
 //   gA3h[v] = sum_i sigma_i * gnb[s_i]              -> gP[v, 2d:3d]
+#ifndef GG_BWD_A_BLOCKS          // A/B builds: resident CTAs per SM edge_bwd_a is compiled for at d <= 128
+#define GG_BWD_A_BLOCKS 2
+#endif
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads, D <= 128 ? 2 : 1)
+__global__ void __launch_bounds__(kNodeThreads, D <= 128 ? GG_BWD_A_BLOCKS : 1)
 edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ src,
                   const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ g_e,
                   const float* __restrict__ P, const float* __restrict__ G, const double* __restrict__ stats_e,
