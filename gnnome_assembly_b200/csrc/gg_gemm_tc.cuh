@@ -797,8 +797,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m0 = (int64_t)mt * BM;
 #pragma unroll
       for (int q = 0; q < QN; ++q) {
-        {
-          // all of the chunk's TMEM loads are issued before the first wait (one round trip instead of EC / 16)
+        if constexpr (!kHeavyEpi) {
+          // all of the chunk's TMEM loads are issued before the first wait (one round trip instead of EC / 16).  Only
+          // for epilogues without a tile of prefetched operands in registers: with them (edge gate: 128 registers of
+          // prefetch) the EC extra live registers spill — measured 138 -> 180 us on gemm_edge_gate.
           uint32_t v[EC / 16][16];
 #pragma unroll
           for (int sub = 0; sub < EC / 16; ++sub)
@@ -816,6 +818,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               stg[tg * TPR + ((4 * sub + j) ^ swz(tg))] =
                   make_float4(__uint_as_float(v[sub][4 * j]), __uint_as_float(v[sub][4 * j + 1]),
                               __uint_as_float(v[sub][4 * j + 2]), __uint_as_float(v[sub][4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int sub = 0; sub < EC / 16; ++sub) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v);
+            if (q == QN - 1 && sub == EC / 16 - 1) {    // accumulator fully read: hand it back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(tmem_empty(acc));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stg[tg * TPR + ((4 * sub + j) ^ swz(tg))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
         }
         group_bar();
         // operands that depend on the column only (bias rows): once per chunk, not once per pass
