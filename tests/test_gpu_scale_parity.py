@@ -239,12 +239,14 @@ def test_one_call_model_path_equals_per_op_path(d, L, bn):
         assert rel_err(s_inf, s) < 1e-6
     assert rel_err(outs[False][0], outs[True][0]) < 1e-6
     assert grads_close(outs[False][1], outs[True][1], rtol=1e-4, atol_frac=1e-5) == []   # (split-K fp32 atomics: order varies run to run)
-    r = oracle(src, dst, g.num_nodes, e, pe)
-    bce_loss(r, y, 1 / 16.5).backward()
+    # the fp64 oracle as the reference: on a default-initialised model several gradients (the last layer's B_1 / B_2) are
+    # tiny differences of large sums, and the fp32 oracle's own summation noise there is as large as ours
+    oracle = oracle.double()
+    r = oracle(src, dst, g.num_nodes, e.double(), pe.double())
+    bce_loss(r, y.double(), 1 / 16.5).backward()
     assert rel_err(outs[False][0], r) < TOL
-    # (default-initialised model: every gradient is small, so the floor for the biases batch norm cancels — true gradient
-    # exactly 0, what comes out is rounding noise — is set a decade higher than in the tests on trained-scale weights)
-    assert grads_close(outs[False][1], {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-4) == []
+    bad = grads_close(outs[False][1], {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-4)
+    assert bad == [], bad
 
 
 def test_gradients_live_in_the_arena_and_survive_a_second_pass():
