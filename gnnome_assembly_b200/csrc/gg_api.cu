@@ -39,6 +39,18 @@ static unsigned node_grid(Kern kern, int64_t n) {
   return (unsigned)blocks;
 }
 
+// Zig-zag traversal.  An E x d tensor (191 MB on the bench graph) does not fit the 126 MB L2, and a producer that
+// writes it front to back followed by a consumer that reads it front to back is the worst case for a recency-managed
+// cache: by the time the consumer starts, the front has been evicted and the back — which IS resident — is evicted
+// before it is reached.  So consecutive E-sized kernels walk their rows / nodes in OPPOSITE directions: the consumer
+// starts where the producer stopped.  Forward of layer l: gemm_edge_gate b, edge_gate_fwd !b, node_agg_fwd b, with
+// b = l & 1 (the next layer's GEMM reads e_out where node_agg_fwd has just finished).  Backward: edge_bwd_a forward,
+// gemm_bwd_e_in reverse, edge_bwd_src forward (every layer: the upstream g_e was written by a reverse GEMM).
+// Per-tile / per-node arithmetic is unchanged.  gg_debug_flags bit 6 (64) switches it off (A/B).
+static thread_local int g_layer_parity = 0;
+void set_layer_parity(int p) { g_layer_parity = p & 1; }
+static inline int zig(int dir) { return (tc::tc_dbg_ref() & 64) ? 0 : (dir & 1); }
+
 // 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
 static int g_tc_mode = 1;
 #ifdef GG_NO_WRES             // A/B builds: per-stage B operand everywhere
@@ -127,6 +139,7 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
                           const float* beta_e, const float* gamma_h, const float* beta_h, float* h_out,
                           float* e_out, float* P, float* t, float* z, float* agg, double* stats, cudaStream_t st) {
   const int64_t N = pl->N, E = pl->E;
+  const int b = g_layer_parity;                   // zig-zag base direction of this layer (see zig())
   GG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * D, st));
   // node projections P = h [A1|A2|A3|B1|B2]^T + b      (gated_gcn_full.py:107-112)
   int rc = linear_fwd("gemm_node_proj", N, 5 * D, D, h_in, D, Wn, D, bn, 0, P, 5 * D, st);
@@ -140,7 +153,7 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
     constexpr int BN = D >= 128 ? 128 : 64;
     if (g_tc_mode && tc::eligible(false, false, E, D, D, D, D, e_in, B3))
       rc = tc::launch<false, false, NORM == GG_NORM_BATCH, false, EpiEdgeGate, tc::NoATx, GG_WRES(D)>(
-          "gemm_edge_gate", e_in, D, B3, D, E, D, D, 1, stats, nullptr, epi, sm_count(), st);
+          "gemm_edge_gate", e_in, D, B3, D, E, D, D, 1, stats, nullptr, epi, sm_count(), st, tc::NoATx{}, nullptr, zig(b));
     else
       rc = launch_gemm<BN, false, true, NORM == GG_NORM_BATCH, false>("gemm_edge_gate", g, epi, 1, st);
     if (rc) return rc;
@@ -168,12 +181,12 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
   } else {
     GG_KERNEL_BEGIN("edge_gate_fwd_kernel", st);
     edge_gate_fwd_kernel<D, NORM><<<node_grid(edge_gate_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
-        N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg);
+        N, E, pl->in_ptr, pl->src, t, e_in, P, stats, gamma_e, beta_e, residual, e_out, agg, zig(b ^ 1));
     GG_KERNEL_END("edge_gate_fwd_kernel", st);
   }
   GG_KERNEL_BEGIN("node_agg_fwd_kernel", st);
   node_agg_fwd_kernel<D, NORM><<<node_grid(node_agg_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
-      N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D);
+      N, pl->out_ptr, pl->out_eid, pl->out_dst, e_out, P, agg, z, stats + 2 * D, zig(b));
   GG_KERNEL_END("node_agg_fwd_kernel", st);
   GG_KERNEL_BEGIN("node_update_fwd_kernel", st);
   node_update_fwd_kernel<D, NORM><<<node_grid(node_update_fwd_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(
@@ -201,7 +214,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   GG_KERNEL_END("node_bwd_apply_kernel", st);
   GG_KERNEL_BEGIN("edge_bwd_a_kernel", st);
   edge_bwd_a_kernel<D, NORM><<<node_grid(edge_bwd_a_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, E, pl->in_ptr, pl->src, t, e_in, g_e, P, G, stats,
-                                                           gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D);
+                                                           gamma_e, beta_e, residual, g_eo, gP, bstats + 2 * D, zig(0));
   GG_KERNEL_END("edge_bwd_a_kernel", st);
   int rc;
   // Batch norm + tensor-core path: g_t is produced inside the bwd-data GEMM (A-operand transform), so the
@@ -213,7 +226,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
     EpiAddMaskT<true, false> epi{g_e_in, (int64_t)D, g_eo, nullptr};
     tc::BnBwdATx atx{stats, bstats + 2 * D, gamma_e, beta_e, 1.0 / (double)E, g_t, (int64_t)D};
     rc = tc::launch<false, true, false, false, EpiAddMaskT<true, false>, tc::BnBwdATx, GG_WRES(D)>(
-        "gemm_bwd_e_in", g_eo, D, B3, D, E, D, D, 1, nullptr, nullptr, epi, sm_count(), st, atx, t);
+        "gemm_bwd_e_in", g_eo, D, B3, D, E, D, D, 1, nullptr, nullptr, epi, sm_count(), st, atx, t, zig(1));
     if (rc) return rc;
   } else {
     GG_KERNEL_BEGIN("edge_bwd_b_kernel", st);
@@ -224,7 +237,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
   GG_KERNEL_BEGIN("edge_bwd_src_kernel", st);
   edge_bwd_src_kernel<D><<<node_grid(edge_bwd_src_kernel<D>, N), kNodeThreads, 0, st>>>(N, pl->out_ptr, pl->out_eid, pl->out_dst, g_t, e_out, G, gP,
                                                        fused_gt ? 1 : 0, E, pl->in_ptr, agg + 4 * N * D, stats,
-                                                       bstats + 2 * D, gamma_e, dgamma_e, dbeta_e);
+                                                       bstats + 2 * D, gamma_e, dgamma_e, dbeta_e, zig(0));
   GG_KERNEL_END("edge_bwd_src_kernel", st);
   // g_e_in = g_eo (residual) + g_t B3 ; dB3 = g_t^T e_in ; db3 = colsum g_t
   if (!fused_gt) {

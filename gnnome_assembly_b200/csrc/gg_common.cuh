@@ -79,6 +79,9 @@ int plan_create_device(const int32_t* src, const int32_t* dst, int64_t N, int64_
     if (_rc) return _rc;      \
   } while (0)
 
+// gg_api.cu: zig-zag base direction of the layer whose forward is issued next (set by the whole-model sequencer)
+void set_layer_parity(int p);
+
 struct SubScratch;
 void free_sub_scratch(SubScratch* s);
 

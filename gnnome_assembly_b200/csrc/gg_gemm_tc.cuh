@@ -122,6 +122,7 @@ struct Args {
   double* col_stats;         // kStats: [2N]
   float* bias_grad;          // kBiasGrad (A MN-major only): [M] sums of A over k
   int dbg;                   // experiment switches (tools/epi_experiment.py): 1 = skip column stats, 2 = skip epilogue prefetches
+  int rev;                   // walk the row tiles from the last to the first (zig-zag traversal, gg_api.cu)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -382,6 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     nt = (int)(w % g.n_tiles);
     const int64_t r = w / g.n_tiles;
     mt = (int)(r % g.m_tiles);
+    if (g.rev) mt = g.m_tiles - 1 - mt;
     sp = (int)(r / g.m_tiles);
   };
   auto k_range = [&](int sp, int64_t& kbeg, int& nkb) {
@@ -974,7 +976,7 @@ inline bool eligible(bool a_mn, bool b_mn, int64_t M, int N, int64_t K, int64_t 
 template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx = NoATx, bool kWRes = false>
 int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
            int splits, double* col_stats, float* bias_grad, const Epi& epi, int num_sms, cudaStream_t st,
-           const ATx& atx = ATx{}, const float* A2 = nullptr) {
+           const ATx& atx = ATx{}, const float* A2 = nullptr, int rev = 0) {
   CUtensorMap tmA, tmB, tmA2;
   int rc;
   if (A_MN) rc = make_map(&tmA, A, M, K, lda, 32, true); else rc = make_map(&tmA, A, K, M, lda, BM, false);
@@ -1008,6 +1010,7 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
   g.col_stats = col_stats;
   g.bias_grad = bias_grad;
   g.dbg = tc_dbg_ref();
+  g.rev = rev;
   const int64_t work = (int64_t)g.m_tiles * g.n_tiles * g.splits;
   const int grid = (int)(work < num_sms ? work : num_sms);
   if (kWRes && (g.n_tiles != 1 || K > 4 * BK || g.splits != 1)) {

@@ -114,7 +114,7 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
                      const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ P,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ beta, int residual, float* __restrict__ e_out,
-                     float* __restrict__ agg) {
+                     float* __restrict__ agg, int rev) {
   constexpr int VPL = D / 32;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
@@ -124,7 +124,8 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
   float* hf = agg;
   float* invden_f = agg + 2 * N * D;
   float* sum_xhat = agg + 4 * N * D;      // sum over in-edges of xhat_e: lets the backward rebuild gB2h per node
-  for (int64_t v = gw; v < N; v += nw) {
+  for (int64_t vi = gw; vi < N; vi += nw) {
+    const int64_t v = rev ? N - 1 - vi : vi;     // zig-zag traversal, see layer_fwd_impl
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> num, den, sx;
     num.fill(0.f); den.fill(0.f); sx.fill(0.f);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kNodeThreads)
 node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ e_out,
                     const float* __restrict__ P, float* __restrict__ agg, float* __restrict__ z,
-                    double* __restrict__ stats_h) {
+                    double* __restrict__ stats_h, int rev) {
   constexpr int VPL = D / 32;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
@@ -203,7 +204,8 @@ node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
   double s1[VPL], s2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
-  for (int64_t u = gw; u < N; u += nw) {
+  for (int64_t ui = gw; ui < N; ui += nw) {
+    const int64_t u = rev ? N - 1 - ui : ui;     // zig-zag traversal, see layer_fwd_impl
     const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> num, den;
     num.fill(0.f); den.fill(0.f);
@@ -390,7 +392,7 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
                   const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ g_e,
                   const float* __restrict__ P, const float* __restrict__ G, const double* __restrict__ stats_e,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int residual,
-                  float* __restrict__ g_eo, float* __restrict__ gP, double* __restrict__ bstats_e) {
+                  float* __restrict__ g_eo, float* __restrict__ gP, double* __restrict__ bstats_e, int rev) {
   constexpr int VPL = D / 32;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
@@ -403,7 +405,8 @@ edge_bwd_a_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
   float f1[VPL], f2[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
-  for (int64_t v = gw; v < N; v += nw) {
+  for (int64_t vi = gw; vi < N; vi += nw) {
+    const int64_t v = rev ? N - 1 - vi : vi;     // zig-zag traversal, see layer_fwd_impl
     const int beg = __ldg(in_ptr + v), end = __ldg(in_ptr + v + 1);
     Row<D> gnf, gdf, a3, acc, sgn;
     acc.fill(0.f); sgn.fill(0.f);
@@ -537,7 +540,7 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
                     const float* __restrict__ e_out, const float* __restrict__ G, float* __restrict__ gP,
                     int fix, int64_t E, const int32_t* __restrict__ in_ptr, const float* __restrict__ sum_xhat,
                     const double* __restrict__ stats_e, const double* __restrict__ bstats_e,
-                    const float* __restrict__ gamma_e, float* __restrict__ dgamma_e, float* __restrict__ dbeta_e) {
+                    const float* __restrict__ gamma_e, float* __restrict__ dgamma_e, float* __restrict__ dbeta_e, int rev) {
   constexpr int VPL = D / 32;
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * kNodeThreads + threadIdx.x) >> 5;
@@ -563,7 +566,8 @@ edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_
     }
   }
   const float* Gf = G;
-  for (int64_t u = gw; u < N; u += nw) {
+  for (int64_t ui = gw; ui < N; ui += nw) {
+    const int64_t u = rev ? N - 1 - ui : ui;     // zig-zag traversal, see layer_fwd_impl
     const int beg = __ldg(out_ptr + u), end = __ldg(out_ptr + u + 1);
     Row<D> acc1, acc2;
     acc1.fill(0.f); acc2.fill(0.f);

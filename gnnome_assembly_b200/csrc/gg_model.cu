@@ -219,10 +219,12 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   // L x GatedGCN                                                                           (processor.py:15-20)
   for (int l = 0; l < dm.L; ++l) {
     const int o = 10 + 8 * l;
+    set_layer_parity(l);                                  // zig-zag traversal: layer l starts where layer l-1 stopped
     GG_TRY(gg_layer_fwd(plan, d, m->norm_kind, 1, ws + w.h[l], ws + w.e[l], P(o), P(o + 1), P(o + 2), P(o + 3), P(o + 4),
                         P(o + 5), P(o + 6), P(o + 7), ws + w.h[l + 1], ws + w.e[l + 1], ws + w.P[l], ws + w.t[l],
                         ws + w.z[l], ws + w.agg[l], reinterpret_cast<double*>(ws + w.stats[l]), stream));
   }
+  set_layer_parity(0);
   // predictor                                                                              (score_predictor.py:12-25)
   GG_KERNEL_BEGIN("score_split_kernel", st);
   score_split_kernel<<<32, 256, 0, st>>>(dm.H, d, P(6), P(7), ws + w.Wq, ws + w.bq, ws + w.W1e);
