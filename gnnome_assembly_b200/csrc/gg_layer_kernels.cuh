@@ -11,6 +11,9 @@
 namespace gg {
 
 constexpr int kNodeThreads = 256;   // 8 warps per CTA
+// resident CTAs per SM the streaming kernels are compiled for (register cap 64 / 85 / 128 per thread): a kernel that
+// drifts from 80 to 86 registers loses a third of its warps (edge_gate_fwd: 143 -> 167 us when that happened)
+template <int D> constexpr int node_min_blocks() { return D <= 64 ? 4 : (D <= 128 ? 3 : 2); }
 
 // ------------------------------------------------------------------ normalisation coefficients
 // NORM == GG_NORM_BATCH: per-channel batch statistics from fp64 sums (biased variance, eps 1e-5)
@@ -109,7 +112,7 @@ __device__ __forceinline__ void block_flush_stats(const double (&s1)[D / 32], co
 //   n = norm_e(t_i); e_out_i = relu(n) + e_in_i; sigma = sigmoid(e_out_i)           (:122-127)
 //   num_f[v] += sigma * A2h[s_i]; den_f[v] += sigma; hf = num_f / (den_f + 1e-6)      (:128-130)
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads)
+__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
 edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ src,
                      const float* __restrict__ t, const float* __restrict__ e_in, const float* __restrict__ P,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -189,7 +192,7 @@ edge_gate_fwd_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, c
 //   num_b[u] += sigma_i * A3h[v_i]; den_b[u] += sigma_i; hb = num_b / (den_b + 1e-6)
 //   z[u] = A1h[u] + hf[u] + hb[u]   and per-channel sum / sum of squares of z for bn_h
 template <int D, int NORM>
-__global__ void __launch_bounds__(kNodeThreads)
+__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
 node_agg_fwd_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ e_out,
                     const float* __restrict__ P, float* __restrict__ agg, float* __restrict__ z,
@@ -534,7 +537,7 @@ edge_bwd_b_kernel(int64_t N, int64_t E, const int32_t* __restrict__ in_ptr, cons
 // With fix != 0 (batch norm, g_t produced inside the bwd-data GEMM): gP[u, 4d:5d] arrives holding
 // S = sum_{in(u)} g_n and is finished here as gB2h[u] = gamma rstd (S - indeg m1 - m2 sum_{in(u)} xhat).
 template <int D>
-__global__ void __launch_bounds__(kNodeThreads)
+__global__ void __launch_bounds__(kNodeThreads, node_min_blocks<D>())
 edge_bwd_src_kernel(int64_t N, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_eid,
                     const int32_t* __restrict__ out_dst, const float* __restrict__ g_t,
                     const float* __restrict__ e_out, const float* __restrict__ G, float* __restrict__ gP,
