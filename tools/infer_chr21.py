@@ -46,7 +46,7 @@ ol = torch.from_numpy(np.trunc(gs.overlap_length)).to(dev)
 sim = torch.from_numpy(gs.overlap_similarity).to(dev)
 y = torch.from_numpy(gs.y).to(dev)
 # lazy initialisation (CUDA module load, cub temp sizing, allocator) is paid on a toy graph, not on the timed one
-gg.GraphPlan(torch.tensor([0, 1, 2]), torch.tensor([1, 2, 0]), 3, dev)
+gg.plan_for(gg.AssemblyGraph(torch.tensor([0, 1, 2]), torch.tensor([1, 2, 0]), 3).to(dev), dev)     # (incl. the cache fingerprint's torch kernels)
 _, t_plan_host = timed(lambda: gg.GraphPlan(g.edges()[0], g.edges()[1], N, dev, host_build=True))     # round-1 builder
 plan, t_plan = timed(lambda: gg.plan_for(g, dev))                                                     # device builder
 e, t_feat = timed(lambda: prep.preprocess_features(ol, sim))                       # utils.py:67-75
