@@ -50,7 +50,7 @@ SIGNATURES = {
     "gg_score_bwd": (_i, [_p, _i, _i] + [_p] * 18),
     "gg_model_workspace_floats": (_i64, [_p, _p, _i]),
     "gg_model_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
-    "gg_model_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p]),
+    "gg_model_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p, _p]),
     "gg_prep_edge_features": (_i, [_i64, _p, _p, _p, _p, _p]),
     "gg_prep_pe": (_i, [_p, _i, C.c_double, _p, _p, _p]),
     "gg_bce_metrics_fwd": (_i, [_i64, _p, _p, C.c_float, _p, _p]),

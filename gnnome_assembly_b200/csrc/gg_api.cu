@@ -47,9 +47,20 @@ static unsigned node_grid(Kern kern, int64_t n) {
 // b = l & 1 (the next layer's GEMM reads e_out where node_agg_fwd has just finished).  Backward: edge_bwd_a forward,
 // gemm_bwd_e_in reverse, edge_bwd_src forward (every layer: the upstream g_e was written by a reverse GEMM).
 // Per-tile / per-node arithmetic is unchanged.  gg_debug_flags bit 6 (64) switches it off (A/B).
+int gg_debug_flags_peek() { return tc::tc_dbg_ref(); }
 static thread_local int g_layer_parity = 0;
 void set_layer_parity(int p) { g_layer_parity = p & 1; }
 static inline int zig(int dir) { return (tc::tc_dbg_ref() & 64) ? 0 : (dir & 1); }
+
+// Weight-gradient GEMMs off the critical path.  dB3 = g_t^T e_in and dWn = gP^T h_in feed nothing but the optimizer: the
+// next layer's backward needs only g_h_in and g_e_in.  When the whole-model sequencer (gg_model_bwd) provides a side
+// stream, gg_layer_bwd forks after edge_bwd_src, runs those two split-K GEMMs there and records `done`; the sequencer
+// alternates the buffers they read (gP, g_t) between layers and joins at the end.  On a full-size graph they then
+// overlap the next layer's node kernels (latency-bound, far from filling the GPU); on mini-batch sub-graphs they leave
+// the kernel-latency chain altogether.
+struct SideCtx { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, done = nullptr; };
+static thread_local SideCtx g_side;
+void set_layer_bwd_side(cudaStream_t side, cudaEvent_t fork, cudaEvent_t done) { g_side.side = side; g_side.fork = fork; g_side.done = done; }
 
 // 1: dense projections with N % 128 == 0 run on the tcgen05 3xTF32 kernel; 0: FFMA everywhere
 static int g_tc_mode = 1;
@@ -244,12 +255,21 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
     rc = linear_bwd_data("gemm_bwd_e_in", E, D, D, g_t, D, B3, D, residual ? g_eo : nullptr, nullptr, g_e_in, D, st);
     if (rc) return rc;
   }
-  rc = linear_bwd_weight("gemm_dB3", E, D, D, g_t, D, e_in, D, dB3, db3, st);
+  // weight gradients: on the side stream when the sequencer gave one (see SideCtx), else in line
+  cudaStream_t wst = st;
+  const SideCtx sc = g_side;
+  if (sc.side != nullptr) {
+    GG_CUDA(cudaEventRecord(sc.fork, st));
+    GG_CUDA(cudaStreamWaitEvent(sc.side, sc.fork, 0));
+    wst = sc.side;
+  }
+  rc = linear_bwd_weight("gemm_dB3", E, D, D, g_t, D, e_in, D, dB3, db3, wst);
   if (rc) return rc;
-  // g_h_in = g_h (residual) + gP Wn ; dWn = gP^T h_in ; dbn = colsum gP
+  rc = linear_bwd_weight("gemm_dWn", N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, wst);
+  if (rc) return rc;
+  if (sc.side != nullptr) GG_CUDA(cudaEventRecord(sc.done, sc.side));
+  // g_h_in = g_h (residual) + gP Wn
   rc = linear_bwd_data("gemm_bwd_h_in", N, 5 * D, D, gP, 5 * D, Wn, D, residual ? g_h : nullptr, nullptr, g_h_in, D, st);
-  if (rc) return rc;
-  rc = linear_bwd_weight("gemm_dWn", N, 5 * D, D, gP, 5 * D, h_in, D, dWn, dbn, st);
   if (rc) return rc;
   // (dgamma / dbeta of both norms are written by node_bwd_apply_kernel and edge_bwd_src_kernel: no launches of their own)
   return GG_OK;

@@ -82,6 +82,10 @@ int plan_create_device(const int32_t* src, const int32_t* dst, int64_t N, int64_
 // gg_api.cu: zig-zag base direction of the layer whose forward is issued next (set by the whole-model sequencer)
 void set_layer_parity(int p);
 
+int gg_debug_flags_peek();      // current gg_debug_flags value (gg_api.cu)
+// gg_api.cu: side stream + events for the weight-gradient GEMMs of the gg_layer_bwd call issued next (null = in line)
+void set_layer_bwd_side(cudaStream_t side, cudaEvent_t fork, cudaEvent_t done);
+
 struct SubScratch;
 void free_sub_scratch(SubScratch* s);
 

@@ -78,7 +78,7 @@ static FwdLayout fwd_layout(const ModelDims& m, bool training) {
 }
 
 struct BwdLayout {
-  int64_t g_int, g_h[2], g_e[2], gP, G, g_eo, g_t, bstats, g_pre, gQ, red, dWq, dbq, dW1e, dWpe4, dW1e4, g_hid;
+  int64_t g_int, g_h[2], g_e[2], gP[2], G, g_eo, g_t[2], bstats, g_pre, gQ, red, dWq, dbq, dW1e, dWpe4, dW1e4, g_hid;
   int64_t total;
 };
 
@@ -88,10 +88,10 @@ static BwdLayout bwd_layout(const ModelDims& m) {
   const int64_t N = m.N > 0 ? m.N : 1, E = m.E > 0 ? m.E : 1, d = m.d;
   w.g_int = b.take(E);
   for (int i = 0; i < 2; ++i) { w.g_h[i] = b.take(N * d); w.g_e[i] = b.take(E * d); }
-  w.gP = b.take(N * 5 * d);
+  // gP and g_t are read by the weight-gradient GEMMs on the side stream while the next layer overwrites them: two sets
+  for (int i = 0; i < 2; ++i) { w.gP[i] = b.take(N * 5 * d); w.g_t[i] = b.take(E * d); }
   w.G = b.take(4 * N * d);
   w.g_eo = b.take(E * d);
-  w.g_t = b.take(E * d);
   w.bstats = b.take(2LL * 4 * d);
   w.g_pre = b.take(E * m.H);
   w.gQ = b.take(N * 2 * m.H);
@@ -236,9 +236,23 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   return GG_OK;
 }
 
+// events of the side-stream protocol: created once per host thread, reused (recording re-arms them)
+struct SideEvents {
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
+  bool ok = false;
+  bool init() {
+    if (ok) return true;
+    ok = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming) == cudaSuccess;
+    return ok;
+  }
+};
+static thread_local SideEvents g_side_events[kMaxDevices];
+
 int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* params, const int64_t* offs, int n_offs,
                  const float* g_scores, const float* ws, float* bws, float* grads, int phase_begin, int phase_end,
-                 void* stream) {
+                 void* stream, void* side_stream) {
   ModelDims dm;
   GG_TRY(check_desc(plan, m, offs, n_offs, &dm));
   GG_REQUIRE(params && ws && bws && grads, "model_bwd: null buffer");
@@ -253,6 +267,13 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   // phases: 0 = predictor, 1 + k = layer L-1-k, L + 1 = encoders.  The gradient of the layer stack's output alternates
   // between the two g_h / g_e buffers; layer l reads buffer (L - l) & 1... and writes the other one.
   if (phase_end > L + 2) phase_end = L + 2;
+  // side stream for the weight-gradient GEMMs: only when this call runs the whole backward (a caller that goes phase by
+  // phase hands each layer's gradients to an all-reduce right after its phase, so they must be complete by then)
+  cudaStream_t side = (cudaStream_t)side_stream;
+  SideEvents& ev = g_side_events[current_device()];
+  const bool use_side = side != nullptr && side != st && phase_begin <= 0 && phase_end == L + 2 && L > 0 &&
+                        !(gg_debug_flags_peek() & 128) && ev.init();       // gg_debug_flags bit 7: in line (A/B)
+  bool pending[2] = {false, false};
   for (int ph = phase_begin < 0 ? 0 : phase_begin; ph < phase_end; ++ph) {
     if (ph == 0) {
       GG_TRY(gg_gather_rows(dm.E, 1, g_scores, pl->perm, bws + b.g_int, stream));
@@ -265,12 +286,20 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
     } else if (ph <= L) {
       const int l = L - ph, o = 10 + 8 * l;
       const int in = (ph - 1) & 1, out = ph & 1;
-      GG_TRY(gg_layer_bwd(plan, d, m->norm_kind, 1, ws + w.h[l], ws + w.e[l], ws + w.e[l + 1], P(o), P(o + 2), P(o + 4),
-                          P(o + 5), P(o + 6), P(o + 7), ws + w.P[l], ws + w.t[l], ws + w.z[l], ws + w.agg[l],
-                          reinterpret_cast<const double*>(ws + w.stats[l]), bws + b.g_h[in], bws + b.g_e[in],
-                          bws + b.g_h[out], bws + b.g_e[out], Gr(o), Gr(o + 1), Gr(o + 2), Gr(o + 3), Gr(o + 4), Gr(o + 5),
-                          Gr(o + 6), Gr(o + 7), bws + b.gP, bws + b.G, bws + b.g_eo, bws + b.g_t,
-                          reinterpret_cast<double*>(bws + b.bstats), stream));
+      const int k = ph & 1;                               // buffer set (gP, g_t) of this layer
+      if (use_side) {
+        if (pending[k]) GG_CUDA(cudaStreamWaitEvent(st, ev.done[k], 0));      // the GEMMs of two layers ago have read set k
+        set_layer_bwd_side(side, ev.fork, ev.done[k]);
+        pending[k] = true;
+      }
+      const int rc = gg_layer_bwd(plan, d, m->norm_kind, 1, ws + w.h[l], ws + w.e[l], ws + w.e[l + 1], P(o), P(o + 2), P(o + 4),
+                                  P(o + 5), P(o + 6), P(o + 7), ws + w.P[l], ws + w.t[l], ws + w.z[l], ws + w.agg[l],
+                                  reinterpret_cast<const double*>(ws + w.stats[l]), bws + b.g_h[in], bws + b.g_e[in],
+                                  bws + b.g_h[out], bws + b.g_e[out], Gr(o), Gr(o + 1), Gr(o + 2), Gr(o + 3), Gr(o + 4),
+                                  Gr(o + 5), Gr(o + 6), Gr(o + 7), bws + b.gP[k], bws + b.G, bws + b.g_eo, bws + b.g_t[k],
+                                  reinterpret_cast<double*>(bws + b.bstats), stream);
+      set_layer_bwd_side(nullptr, nullptr, nullptr);
+      if (rc) return rc;
     } else {
       const int in = L & 1;                              // where the gradient w.r.t. (h0, e0) ended up
       const float* g_h0 = bws + b.g_h[in];
@@ -290,6 +319,10 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
       GG_TRY(gg_linear_bwd_weight(dm.N, d, dm.node_k4, g_h0, ws + w.pe4, bws + b.dWpe4, Gr(1), stream));
       GG_TRY(copy_rows("unpad_weight_kernel", d, dm.node_k4, dm.node_in, bws + b.dWpe4, nullptr, Gr(0), st));
     }
+  }
+  if (use_side) {                                         // join: every weight gradient is complete on `stream`
+    for (int k = 0; k < 2; ++k)
+      if (pending[k]) GG_CUDA(cudaStreamWaitEvent(st, ev.done[k], 0));
   }
   return GG_OK;
 }

@@ -355,6 +355,17 @@ def score_predictor(plan, x, e, W1, b1, W2, b2, arena=None):
 
 
 # ----------------------------------------------------------------------------------- whole model, one call each way
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the weight-gradient GEMMs of gg_model_bwd (forked and joined inside the call)."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _ModelDesc(_lib.C.Structure):
     _fields_ = [(n, _lib.C.c_int32) for n in ("d", "layers", "hidden_edge", "hidden_score", "norm_kind", "node_in",
                                                "edge_in", "reserved")]
@@ -426,9 +437,11 @@ class _Model(torch.autograd.Function):
                           dtype=torch.float32)
         grads = arena.tensor()
 
+        side = _side_stream(g.device)
+
         def run(lo, hi, st):
             check(lib.gg_model_bwd(plan.handle, C.byref(desc), ptr(flat), offs, n, ptr(g), ptr(ws), ptr(bws), ptr(grads),
-                                   lo, hi, st), "gg_model_bwd")
+                                   lo, hi, st, side.cuda_stream), "gg_model_bwd")
 
         with _on(g, ws, flat, plan=plan) as st:
             if arena.on_segment_ready is None:

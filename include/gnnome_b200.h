@@ -44,7 +44,9 @@ int gg_set_tc_mode(int mode);
 /* experiment switches for the tensor-core GEMM epilogue (tools/epi_experiment.py): bit 0 skips the column
  * statistics, bit 1 skips the epilogue operand prefetch (WRONG RESULTS; timing experiments only); bit 3 (8) runs
  * the forward edge-gate pass with its streamed operands staged through shared memory by cp.async.bulk (correct
- * results; measured slower than the default register-staged kernel, kept as an experiment). Returns old. */
+ * results; measured slower than the default register-staged kernel, kept as an experiment); bit 6 (64) switches the
+ * zig-zag traversal of consecutive E-sized kernels off, bit 7 (128) keeps the weight-gradient GEMMs of gg_model_bwd on
+ * the main stream (same results, A/B timing). Returns old. */
 int gg_debug_flags(int flags);
 /* Trace builds only (-DGG_TC_TRACE, tools/ab_build.sh + tools/tc_trace.py): per-role clock64 totals of the tcgen05
  * GEMM (cycles inside each mbarrier wait / per role), summed over CTAs since the last reset; synchronises the
@@ -191,7 +193,10 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
  * Workspaces are caller-owned: gg_model_workspace_floats(plan, m, which) floats, which = 0 forward that keeps what the
  * backward reads, 1 forward for inference (layer buffers reused), 2 backward scratch.  gg_model_bwd runs the phases
  * [phase_begin, phase_end) of: 0 predictor, 1 + k layer L-1-k, L + 1 encoders — a caller that all-reduces gradients
- * per layer issues one call per phase; 0 .. L + 2 does everything. */
+ * per layer issues one call per phase; 0 .. L + 2 does everything.
+ * side_stream (may be NULL): a second caller-owned stream.  When the call runs the whole backward, the weight-gradient
+ * GEMMs of every layer (dB3, dWn: nothing downstream reads them) are forked onto it and joined back into `stream`
+ * before the call returns its last launch, so on return everything is ordered on `stream` as usual. */
 typedef struct gg_model_desc {
   int32_t d;            /* hidden_features: 64, 128 or 256 */
   int32_t layers;       /* num_layers */
@@ -207,7 +212,7 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
                  const float* e, const float* pe, int training, float* ws, float* scores, void* stream);
 int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* params, const int64_t* offs, int n_offs,
                  const float* g_scores, const float* ws, float* bws, float* grads, int phase_begin, int phase_end,
-                 void* stream);
+                 void* stream, void* side_stream);
 
 /* ---- input preparation ("next" row 1 of SURVEY.md 8f) ----------------------------------------------
  * gg_prep_edge_features replaces utils.preprocess_graph, utils.py:70-74: e[E,2] = z-scored overlap_length,
