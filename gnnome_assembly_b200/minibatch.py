@@ -107,13 +107,26 @@ class ClusterGCNSampler:
         self._resident = g if _is_resident(g, self.device) else g.to(self.device)
         if self._resident is not g:
             _PLAN_CACHE[self._resident] = plan
+        # Sampling runs on a stream of its own.  gg_subplan_count has to bring one integer to the host, i.e. it
+        # synchronises the stream it runs on: on the training stream that wait would cover the previous batch's whole
+        # backward + optimizer step and serialise host and device (batch time = host time + device time).  Sampling only
+        # reads static data (parent plan, resident features), so it needs nothing from the training stream.
+        torch.cuda.synchronize(self.device)                     # the resident copies above are complete
+        self._stream = torch.cuda.Stream(device=self.device)
 
     def sample(self, g, partition_ids):
         ids = [int(i) for i in torch.as_tensor(partition_ids).reshape(-1).tolist()]
         off = self.partition_offset
         parts = [self.partition_node_ids[off[i]:off[i + 1]] for i in ids]
-        nodes = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=self.device)
-        return node_subgraph(self._resident, nodes, self.device)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._stream):
+            nodes = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=self.device)
+            sub = node_subgraph(self._resident, nodes, self.device)
+        main.wait_stream(self._stream)                          # the consumer (training stream) sees the finished batch
+        for t in (*sub.edges(), *sub.ndata.values(), *sub.edata.values(), getattr(_PLAN_CACHE.get(sub), "_slab", None)):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(main)                           # allocated on the sampling stream, consumed on `main`
+        return sub
 
 
 def _is_resident(g, device):
@@ -142,5 +155,11 @@ class DataLoader:
             yield idx[b * self.batch_size:(b + 1) * self.batch_size]
 
     def __iter__(self):
+        # one batch ahead: the sub-graph of batch k + 1 is cut (on the sampler's stream) while batch k trains
+        nxt = None
         for batch in self.batches():
-            yield self.sampler.sample(self.g, batch)
+            cur, nxt = nxt, self.sampler.sample(self.g, batch)
+            if cur is not None:
+                yield cur
+        if nxt is not None:
+            yield nxt
