@@ -304,6 +304,28 @@ def run_ours(args):
         del oracle, twin, loss0
         torch.cuda.synchronize()
 
+    # ---- data-parallel gate (N > 1): every rank holds the same graph and the same weights, so the all-reduced MEAN
+    # gradient must equal the local one.  Checks the ordering of the three streams involved (backward, side stream of the
+    # weight-gradient GEMMs, NCCL stream) under the real collective, before anything is timed.
+    dp_check = None
+    if world > 1:
+        import copy
+        twin = copy.deepcopy(model)
+        loss_a = bce_loss(twin(graph, None, d_e, d_pe), d_y)
+        loss_a.backward()
+        local = [p.grad.clone() for p in twin.parameters()]
+        twin2 = copy.deepcopy(model)
+        tsync = ArenaSync(twin2)
+        loss_b = bce_loss(twin2(graph, None, d_e, d_pe), d_y)
+        loss_b.backward()
+        tsync.finish()
+        torch.cuda.synchronize()
+        scale = max(float(g_.abs().max()) for g_ in local)
+        worst = max(float((p.grad - g_).abs().max()) for p, g_ in zip(twin2.parameters(), local))
+        dp_check = {"max_abs_diff_reduced_vs_local": worst, "largest_gradient": scale}
+        assert worst <= 1e-4 * scale, f"bench: all-reduced gradients differ from the local ones: {dp_check}"
+        del twin, twin2, tsync, local
+
     graphed = None
     launches_per_step = None
     if use_graph:
@@ -455,6 +477,7 @@ def run_ours(args):
         "kernels": kernels,
         "clocks": clocks,
         "parity_check": parity,
+        "dp_check": dp_check,
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,

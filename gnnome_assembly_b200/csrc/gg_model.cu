@@ -240,6 +240,7 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
 struct SideEvents {
   cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
   bool ok = false;
+  bool pending[2] = {false, false};      // side GEMMs reading buffer set k are in flight (persists across phase calls)
   bool init() {
     if (ok) return true;
     ok = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -267,13 +268,14 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   // phases: 0 = predictor, 1 + k = layer L-1-k, L + 1 = encoders.  The gradient of the layer stack's output alternates
   // between the two g_h / g_e buffers; layer l reads buffer (L - l) & 1... and writes the other one.
   if (phase_end > L + 2) phase_end = L + 2;
-  // side stream for the weight-gradient GEMMs: only when this call runs the whole backward (a caller that goes phase by
-  // phase hands each layer's gradients to an all-reduce right after its phase, so they must be complete by then)
+  // side stream for the weight-gradient GEMMs.  A caller that goes phase by phase (data-parallel all-reduce per layer
+  // bucket) must make its collective wait for `side_stream` as well as `stream`; the join into `stream` happens in the
+  // call that runs the last phase.
   cudaStream_t side = (cudaStream_t)side_stream;
   SideEvents& ev = g_side_events[current_device()];
-  const bool use_side = side != nullptr && side != st && phase_begin <= 0 && phase_end == L + 2 && L > 0 &&
-                        !(gg_debug_flags_peek() & 128) && ev.init();       // gg_debug_flags bit 7: in line (A/B)
-  bool pending[2] = {false, false};
+  const bool use_side = side != nullptr && side != st && L > 0 && !(gg_debug_flags_peek() & 128) && ev.init();   // bit 7: in line (A/B)
+  bool (&pending)[2] = ev.pending;
+  if (phase_begin <= 0) pending[0] = pending[1] = false;
   for (int ph = phase_begin < 0 ? 0 : phase_begin; ph < phase_end; ++ph) {
     if (ph == 0) {
       GG_TRY(gg_gather_rows(dm.E, 1, g_scores, pl->perm, bws + b.g_int, stream));
@@ -320,9 +322,9 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
       GG_TRY(copy_rows("unpad_weight_kernel", d, dm.node_k4, dm.node_in, bws + b.dWpe4, nullptr, Gr(0), st));
     }
   }
-  if (use_side) {                                         // join: every weight gradient is complete on `stream`
+  if (use_side && phase_end == L + 2) {                    // join: every weight gradient is complete on `stream`
     for (int k = 0; k < 2; ++k)
-      if (pending[k]) GG_CUDA(cudaStreamWaitEvent(st, ev.done[k], 0));
+      if (pending[k]) { GG_CUDA(cudaStreamWaitEvent(st, ev.done[k], 0)); pending[k] = false; }
   }
   return GG_OK;
 }

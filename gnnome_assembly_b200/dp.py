@@ -138,7 +138,9 @@ class ArenaSync:
             if comm is None:
                 self._reduce(buf)
             else:
+                from .functional import _side_stream
                 comm.wait_stream(torch.cuda.current_stream(buf.device))
+                comm.wait_stream(_side_stream(buf.device))      # the layers' weight-gradient GEMMs run there (gg_model_bwd)
                 with torch.cuda.stream(comm):
                     self._reduce(buf)
 

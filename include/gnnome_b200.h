@@ -194,9 +194,10 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
  * backward reads, 1 forward for inference (layer buffers reused), 2 backward scratch.  gg_model_bwd runs the phases
  * [phase_begin, phase_end) of: 0 predictor, 1 + k layer L-1-k, L + 1 encoders — a caller that all-reduces gradients
  * per layer issues one call per phase; 0 .. L + 2 does everything.
- * side_stream (may be NULL): a second caller-owned stream.  When the call runs the whole backward, the weight-gradient
- * GEMMs of every layer (dB3, dWn: nothing downstream reads them) are forked onto it and joined back into `stream`
- * before the call returns its last launch, so on return everything is ordered on `stream` as usual. */
+ * side_stream (may be NULL): a second caller-owned stream.  The weight-gradient GEMMs of every layer (dB3, dWn: nothing
+ * downstream reads them) are forked onto it and joined back into `stream` by the call that runs the last phase, so
+ * after a whole backward everything is ordered on `stream` as usual; a caller that consumes a layer's gradients between
+ * phases must order that consumer after BOTH streams. */
 typedef struct gg_model_desc {
   int32_t d;            /* hidden_features: 64, 128 or 256 */
   int32_t layers;       /* num_layers */
