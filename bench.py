@@ -384,12 +384,17 @@ def run_ours(args):
 
     # per-kernel pass: CUDA event pair around every launch, on the launching stream (not the timed region)
     # (every rank runs these steps — they contain the gradient all-reduce — but only rank 0 records events)
+    # (the weight-gradient GEMMs are kept on the main stream for this pass — gg_debug_flags bit 7 — so that every event
+    # pair brackets ONE kernel running alone; in the timed region above they overlap the next layer's node kernels)
+    old_flags = _lib.lib().gg_debug_flags(0)
+    _lib.lib().gg_debug_flags(old_flags | 128)
     _lib.profile(rank == 0)
     for _ in range(3):
         flush.zero_()
         step(d_e, d_pe, d_y)
     torch.cuda.synchronize()
     _lib.profile(False)
+    _lib.lib().gg_debug_flags(old_flags)
     prof = _lib.profile_report() if rank == 0 else {}
 
     # max over ranks, sum of edges
