@@ -310,11 +310,13 @@ def run_ours(args):
     dp_check = None
     if world > 1:
         import copy
-        twin = copy.deepcopy(model)
+        hook, model.arena_hook = model.arena_hook, None          # (a deep copy would carry the sync's hook along)
+        twin, twin2 = copy.deepcopy(model), copy.deepcopy(model)
+        model.arena_hook = hook
         loss_a = bce_loss(twin(graph, None, d_e, d_pe), d_y)
         loss_a.backward()
+        torch.cuda.synchronize()
         local = [p.grad.clone() for p in twin.parameters()]
-        twin2 = copy.deepcopy(model)
         tsync = ArenaSync(twin2)
         loss_b = bce_loss(twin2(graph, None, d_e, d_pe), d_y)
         loss_b.backward()
