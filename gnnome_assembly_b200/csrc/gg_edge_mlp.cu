@@ -11,9 +11,11 @@
 
 namespace gg {
 
-constexpr int kMlpThreads = 384;         // 12 warps: 3 per scheduler (the row loop is a chain of dependent FMAs / shuffles)
+constexpr int kMlpThreads = 256;         // 8 warps, TWO rows per warp and iteration (see below)
 constexpr int kMlpHid = 16, kMlpK = 4;       // hidden_edge_features = 16 (hyperparameters.py:11), edge_features 2 padded to 4
 
+// Round 2: the kernel was bound by the shared-memory reads of W2 (ncu: l1tex 87 % busy, DRAM 13 %): every row re-read the
+// lane's 16 x VPL weights.  Each warp now takes TWO rows per iteration and reads every W2 value once for both.
 template <int D>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restrict__ hid, const float* __restrict__ e,
@@ -41,35 +43,47 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
   for (int j = 0; j < kMlpK; ++j) a1[j] = 0.f;
   const int my_k = lane >> 1;                                // the hidden unit this lane pair ends up owning
 
-  // software pipeline: the next row's operands are requested before the current row is processed (8 warps per
-  // SM cannot hide a DRAM round trip per row on their own)
-  Row<D> gn;
-  float4 hn[H / 4], en;
-  float hkn;
-  auto fetch = [&](int64_t row) {
-    gn.load_stream(g + row * D, lane);
+  // rows r0 = it, r1 = it + nw of this warp's stride-2nw sequence; a missing second row contributes zeros.
+  // Software pipeline: the next pair's operands are requested before the current pair is processed (8 warps per SM
+  // cannot hide a DRAM round trip per pair on their own).
+  Row<D> g0n, g1n;
+  float4 h0n[H / 4], h1n[H / 4], e0n, e1n;
+  float hk0n, hk1n;
+  auto fetch = [&](int64_t r0) {
+    const int64_t r1 = r0 + nw;
+    const bool two = r1 < E;
+    g0n.load_stream(g + r0 * D, lane);
+    if (two) g1n.load_stream(g + r1 * D, lane); else g1n.fill(0.f);
 #pragma unroll
-    for (int k = 0; k < H / 4; ++k) hn[k] = __ldg(reinterpret_cast<const float4*>(hid + row * H) + k);   // same address in every lane
-    en = __ldg(reinterpret_cast<const float4*>(e + row * kMlpK));
-    hkn = __ldg(hid + row * H + my_k);
+    for (int k = 0; k < H / 4; ++k) {                        // same address in every lane (broadcast)
+      h0n[k] = __ldg(reinterpret_cast<const float4*>(hid + r0 * H) + k);
+      h1n[k] = two ? __ldg(reinterpret_cast<const float4*>(hid + r1 * H) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    e0n = __ldg(reinterpret_cast<const float4*>(e + r0 * kMlpK));
+    e1n = two ? __ldg(reinterpret_cast<const float4*>(e + r1 * kMlpK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    hk0n = __ldg(hid + r0 * H + my_k);
+    hk1n = two ? __ldg(hid + r1 * H + my_k) : 0.f;
   };
   if (gw < E) fetch(gw);
-  for (int64_t row = gw; row < E; row += nw) {
-    const Row<D> gr = gn;
-    float h[H];
+  for (int64_t r0 = gw; r0 < E; r0 += 2 * nw) {
+    const Row<D> g0 = g0n, g1 = g1n;
+    float h0[H], h1[H];
 #pragma unroll
-    for (int k = 0; k < H / 4; ++k) { h[4 * k] = hn[k].x; h[4 * k + 1] = hn[k].y; h[4 * k + 2] = hn[k].z; h[4 * k + 3] = hn[k].w; }
-    const float4 ev = en;
-    const float hk = hkn;
-    if (row + nw < E) fetch(row + nw);
-    float v[H];
+    for (int k = 0; k < H / 4; ++k) {
+      h0[4 * k] = h0n[k].x; h0[4 * k + 1] = h0n[k].y; h0[4 * k + 2] = h0n[k].z; h0[4 * k + 3] = h0n[k].w;
+      h1[4 * k] = h1n[k].x; h1[4 * k + 1] = h1n[k].y; h1[4 * k + 2] = h1n[k].z; h1[4 * k + 3] = h1n[k].w;
+    }
+    const float4 e0 = e0n, e1 = e1n;
+    const float hk0 = hk0n, hk1 = hk1n;
+    if (r0 + 2 * nw < E) fetch(r0 + 2 * nw);
+    float v0[H], v1[H];
 #pragma unroll
-    for (int k = 0; k < H; ++k) v[k] = 0.f;
+    for (int k = 0; k < H; ++k) { v0[k] = 0.f; v1[k] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) ab2[i] += gr.v[i];
+    for (int i = 0; i < VPL; ++i) ab2[i] += g0.v[i] + g1.v[i];
 #pragma unroll
     for (int k = 0; k < H; ++k) {
-      Row<D> wk;                                             // W2[c][k] for this lane's channels (conflict-free LDS)
+      Row<D> wk;                                             // W2[c][k] for this lane's channels (conflict-free LDS), read ONCE for both rows
       if constexpr (D == 64) {
         const float2 x = reinterpret_cast<const float2*>(wsh + k * D)[lane];
         wk.v[0] = x.x; wk.v[1] = x.y;
@@ -82,8 +96,10 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
       }
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        v[k] = fmaf(gr.v[i], wk.v[i], v[k]);                 // partial (g W2)[k] over this lane's channels
-        a2[i][k] = fmaf(gr.v[i], h[k], a2[i][k]);            // dW2[c][k] += g[c] hid[k]
+        v0[k] = fmaf(g0.v[i], wk.v[i], v0[k]);               // partial (g W2)[k] over this lane's channels
+        v1[k] = fmaf(g1.v[i], wk.v[i], v1[k]);
+        a2[i][k] = fmaf(g0.v[i], h0[k], a2[i][k]);           // dW2[c][k] += g[c] hid[k]
+        a2[i][k] = fmaf(g1.v[i], h1[k], a2[i][k]);
       }
     }
     // transpose-reduce: after the step with offset o, a lane keeps the half of its values selected by (lane & o)
@@ -92,16 +108,21 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
       const bool up = (lane & o) != 0;
 #pragma unroll
       for (int j = 0; j < n; ++j) {
-        const float send = up ? v[j] : v[j + n];
-        const float keep = up ? v[j + n] : v[j];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        const float s0 = up ? v0[j] : v0[j + n], k0 = up ? v0[j + n] : v0[j];
+        const float s1 = up ? v1[j] : v1[j + n], k1 = up ? v1[j + n] : v1[j];
+        v0[j] = k0 + __shfl_xor_sync(0xffffffffu, s0, o);
+        v1[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
       }
     }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);           // both lanes of the pair: (g W2)[lane >> 1]
-    const float gh = hk > 0.f ? v[0] : 0.f;                  // ReLU backward
-    a1[0] = fmaf(gh, ev.x, a1[0]); a1[1] = fmaf(gh, ev.y, a1[1]);
-    a1[2] = fmaf(gh, ev.z, a1[2]); a1[3] = fmaf(gh, ev.w, a1[3]);
-    ab1 += gh;
+    v0[0] += __shfl_xor_sync(0xffffffffu, v0[0], 1);         // both lanes of the pair: (g W2)[lane >> 1]
+    v1[0] += __shfl_xor_sync(0xffffffffu, v1[0], 1);
+    const float gh0 = hk0 > 0.f ? v0[0] : 0.f;               // ReLU backward
+    const float gh1 = hk1 > 0.f ? v1[0] : 0.f;
+    a1[0] = fmaf(gh0, e0.x, a1[0]); a1[1] = fmaf(gh0, e0.y, a1[1]);
+    a1[2] = fmaf(gh0, e0.z, a1[2]); a1[3] = fmaf(gh0, e0.w, a1[3]);
+    a1[0] = fmaf(gh1, e1.x, a1[0]); a1[1] = fmaf(gh1, e1.y, a1[1]);
+    a1[2] = fmaf(gh1, e1.z, a1[2]); a1[3] = fmaf(gh1, e1.w, a1[3]);
+    ab1 += gh0 + gh1;
   }
 
   __syncthreads();
