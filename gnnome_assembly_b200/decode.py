@@ -13,6 +13,16 @@ CDF on the device; `start_edges=` pins them for reproducible runs and parity tes
 iteration concurrently, one warp each (`gg_decode_walks`) -> pick the walk reconstructing the longest sequence
 -> `gg_decode_commit` adds it, its strand mates and the jumped-over nodes to the visited bitmap.  One small D2H
 per iteration (lengths), one for the chosen walk.  There is no CPU path.
+
+Deviations from the reference, on purpose:
+  * self loops: the reference drops them with dgl.remove_self_loop (inference.py:187), which renumbers the edges while
+    its `edges` dictionary keeps the old ids; here a self loop is left out of the successor / predecessor lists and gets
+    sampling weight 0, and every other edge keeps its id;
+  * a walk is cut, and the call raises, when it exceeds N nodes: the single-neighbour shortcut (inference.py:42-44,
+    :65-67) skips the visited check, so on a cycle of single-neighbour nodes the reference never returns.  A finite walk
+    that legitimately revisits nodes through that shortcut and grows past N nodes is reported the same way (the walk
+    buffer holds 2N entries per walk: N forwards, N backwards);
+  * when no edge is left to sample from, the loop ends; the reference raises (Categorical over zero edges).
 """
 from __future__ import annotations
 
