@@ -40,3 +40,29 @@ def test_ring_protocol_simulation():
     exec(compile(src, spec.origin, "exec"), ns)
     for seed in range(300):
         assert ns["sim"](seed)
+
+
+def test_gemm_barrier_protocol_simulation():
+    """tools/gemm_protocol_sim.py: the stage / accumulator mbarrier protocol of the tcgen05 GEMM with the g_t bulk store
+    (empty(s) takes two arrivals: MMA commit + store thread) survives random interleavings; the round-1 protocol (stage
+    released by the MMA commit alone) is caught overwriting a stage that the store still reads."""
+    spec_path = os.path.join(ROOT, "tools", "gemm_protocol_sim.py")
+    src = open(spec_path).read()
+    ns = {"__name__": "gemm_protocol_sim"}
+    exec(compile(src, spec_path, "exec"), ns)
+    import random
+    for seed in range(300):
+        assert ns["sim"](seed, stages=random.Random(seed).choice([2, 3]), tiles=random.Random(seed + 1).randint(1, 9),
+                         kblocks=random.Random(seed + 2).choice([1, 4, 8]))
+    bad = src.replace("empty = [Bar(2) for _ in range(stages)]", "empty = [Bar(1) for _ in range(stages)]") \
+             .replace("            store_done[s] = True\n            empty[s].arrive()", "            store_done[s] = True")
+    assert bad != src
+    ns2 = {"__name__": "mutant"}
+    exec(compile(bad, spec_path, "exec"), ns2)
+    caught = 0
+    for seed in range(60):
+        try:
+            ns2["sim"](seed)
+        except AssertionError:
+            caught += 1
+    assert caught > 0
