@@ -50,6 +50,11 @@ static unsigned node_grid(Kern kern, int64_t n) {
 int gg_debug_flags_peek() { return tc::tc_dbg_ref(); }
 static thread_local int g_layer_parity = 0;
 void set_layer_parity(int p) { g_layer_parity = p & 1; }
+// gg_model_* zeroes every accumulator of a pass (statistics, split-K weight gradients) with ONE memset up front and sets
+// this; the entry points below then skip their own memsets (60 memset nodes per training step otherwise).
+static thread_local bool g_prezeroed = false;
+void set_prezeroed(bool on) { g_prezeroed = on; }
+bool prezeroed() { return g_prezeroed; }
 static inline int zig(int dir) { return (tc::tc_dbg_ref() & 64) ? 0 : (dir & 1); }
 
 // Weight-gradient GEMMs off the critical path.  dB3 = g_t^T e_in and dWn = gP^T h_in feed nothing but the optimizer: the
@@ -118,8 +123,10 @@ static int linear_bwd_data(const char* tag, int64_t M, int N, int K, const float
 // dW[N,K] = dY[M,N]^T X[M,K] ; db[N] = colsum(dY)       (dW, db zeroed here)
 static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const float* dY, int64_t lddy, const float* X, int64_t ldx,
                              float* dW, float* db, cudaStream_t st) {
-  GG_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
-  if (db) GG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+  if (!g_prezeroed) {
+    GG_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
+    if (db) GG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+  }
   if (M <= 0) return GG_OK;
   GemmArgs g{};
   g.A = dY; g.lda = lddy; g.B = X; g.ldb = ldx; g.M = N; g.N = K; g.K = M;
@@ -151,7 +158,7 @@ static int layer_fwd_impl(const Plan* pl, int residual, const float* h_in, const
                           float* e_out, float* P, float* t, float* z, float* agg, double* stats, cudaStream_t st) {
   const int64_t N = pl->N, E = pl->E;
   const int b = g_layer_parity;                   // zig-zag base direction of this layer (see zig())
-  GG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * D, st));
+  if (!g_prezeroed) GG_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * D, st));
   // node projections P = h [A1|A2|A3|B1|B2]^T + b      (gated_gcn_full.py:107-112)
   int rc = linear_fwd("gemm_node_proj", N, 5 * D, D, h_in, D, Wn, D, bn, 0, P, 5 * D, st);
   if (rc) return rc;
@@ -215,7 +222,7 @@ static int layer_bwd_impl(const Plan* pl, int residual, const float* h_in, const
                           float* db3, float* dgamma_e, float* dbeta_e, float* dgamma_h, float* dbeta_h,
                           float* gP, float* G, float* g_eo, float* g_t, double* bstats, cudaStream_t st) {
   const int64_t N = pl->N, E = pl->E;
-  GG_CUDA(cudaMemsetAsync(bstats, 0, sizeof(double) * 4 * D, st));
+  if (!g_prezeroed) GG_CUDA(cudaMemsetAsync(bstats, 0, sizeof(double) * 4 * D, st));
   GG_KERNEL_BEGIN("node_bwd_reduce_kernel", st);
   node_bwd_reduce_kernel<D, NORM><<<node_grid(node_bwd_reduce_kernel<D, NORM>, N), kNodeThreads, 0, st>>>(N, z, g_h, stats + 2 * D, gamma_h, beta_h, bstats);
   GG_KERNEL_END("node_bwd_reduce_kernel", st);
@@ -481,7 +488,7 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = pl->N, E = pl->E;
-  GG_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * (2 * H + 1), st));
+  if (!g_prezeroed) GG_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * (2 * H + 1), st));
   {
     int64_t blocks = (E + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;

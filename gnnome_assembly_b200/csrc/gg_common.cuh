@@ -81,6 +81,8 @@ int plan_create_device(const int32_t* src, const int32_t* dst, int64_t N, int64_
 
 // gg_api.cu: zig-zag base direction of the layer whose forward is issued next (set by the whole-model sequencer)
 void set_layer_parity(int p);
+void set_prezeroed(bool on);    // accumulators were zeroed by the caller (gg_model_*): skip the per-op memsets
+bool prezeroed();
 
 int gg_debug_flags_peek();      // current gg_debug_flags value (gg_api.cu)
 // gg_api.cu: side stream + events for the weight-gradient GEMMs of the gg_layer_bwd call issued next (null = in line)

@@ -161,10 +161,12 @@ extern "C" int gg_edge_mlp_bwd(int64_t E, int d, int hidden, int K, const float*
   GG_REQUIRE(W2 && dW1 && db1 && dW2 && db2, "edge_mlp_bwd: null parameter / output");
   GG_REQUIRE(E == 0 || (g && hid && e), "edge_mlp_bwd: null edge buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  GG_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)d * hidden, st));
-  GG_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * (size_t)d, st));
-  GG_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)hidden * K, st));
-  GG_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * (size_t)hidden, st));
+  if (!prezeroed()) {                                   // gg_model_bwd zeroes the whole gradient arena in one memset
+    GG_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)d * hidden, st));
+    GG_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * (size_t)d, st));
+    GG_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)hidden * K, st));
+    GG_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * (size_t)hidden, st));
+  }
   if (E == 0) return GG_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

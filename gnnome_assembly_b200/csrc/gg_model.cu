@@ -41,6 +41,7 @@ struct ModelDims {
 struct FwdLayout {
   int64_t e4, pe4, Wpe4, W1e4, hid_e, Wq, bq, W1e, Q, hid_s, score_int;
   std::vector<int64_t> h, e, P, t, z, agg, stats;      // h / e: L + 1 entries (layer inputs, last = outputs)
+  int64_t stats_all, stats_floats;                     // the per-layer statistics as one block
   int64_t total;
 };
 
@@ -63,15 +64,18 @@ static FwdLayout fwd_layout(const ModelDims& m, bool training) {
   std::vector<int64_t> hs(slots), es(slots);
   for (int i = 0; i < slots; ++i) { hs[i] = b.take(N * d); es[i] = b.take(E * d); }
   const int sets = training ? m.L : 1;
-  std::vector<int64_t> P(sets), t(sets), z(sets), agg(sets), st(sets);
+  std::vector<int64_t> P(sets), t(sets), z(sets), agg(sets);
   for (int i = 0; i < sets; ++i) {
     P[i] = b.take(N * 5 * d); t[i] = b.take(E * d); z[i] = b.take(N * d); agg[i] = b.take(5 * N * d);
-    st[i] = b.take(2LL * 4 * d);                        // 4d doubles
   }
+  // batch statistics: 4d doubles per layer, all layers contiguous (one memset per pass zeroes them)
+  w.stats_all = b.take(2LL * 4 * d * (m.L > 0 ? m.L : 1));
+  w.stats_floats = 2LL * 4 * d * m.L;
   for (int l = 0; l <= m.L; ++l) { w.h.push_back(hs[training ? l : (l & 1)]); w.e.push_back(es[training ? l : (l & 1)]); }
   for (int l = 0; l < m.L; ++l) {
     const int s = training ? l : 0;
-    w.P.push_back(P[s]); w.t.push_back(t[s]); w.z.push_back(z[s]); w.agg.push_back(agg[s]); w.stats.push_back(st[s]);
+    w.P.push_back(P[s]); w.t.push_back(t[s]); w.z.push_back(z[s]); w.agg.push_back(agg[s]);
+    w.stats.push_back(w.stats_all + 2LL * 4 * d * l);
   }
   w.total = b.off;
   return w;
@@ -79,6 +83,7 @@ static FwdLayout fwd_layout(const ModelDims& m, bool training) {
 
 struct BwdLayout {
   int64_t g_int, g_h[2], g_e[2], gP[2], G, g_eo, g_t[2], bstats, g_pre, gQ, red, dWq, dbq, dW1e, dWpe4, dW1e4, g_hid;
+  int64_t zero_begin, zero_end;                        // accumulators (bstats per layer .. dW1e4): one memset per pass
   int64_t total;
 };
 
@@ -92,15 +97,17 @@ static BwdLayout bwd_layout(const ModelDims& m) {
   for (int i = 0; i < 2; ++i) { w.gP[i] = b.take(N * 5 * d); w.g_t[i] = b.take(E * d); }
   w.G = b.take(4 * N * d);
   w.g_eo = b.take(E * d);
-  w.bstats = b.take(2LL * 4 * d);
   w.g_pre = b.take(E * m.H);
   w.gQ = b.take(N * 2 * m.H);
+  w.zero_begin = b.off;
+  w.bstats = b.take(2LL * 4 * d * (m.L > 0 ? m.L : 1));       // 4d doubles per layer
   w.red = b.take(2LL * (2 * m.H + 1));
   w.dWq = b.take(2LL * m.H * d);
   w.dbq = b.take(2LL * m.H);
   w.dW1e = b.take((int64_t)m.H * d);
   w.dWpe4 = b.take((int64_t)d * m.node_k4);
   w.dW1e4 = b.take((int64_t)m.he * m.edge_k4);
+  w.zero_end = b.off;
   w.g_hid = b.take(E * m.he);
   w.total = b.off;
   return w;
@@ -172,6 +179,45 @@ static int check_desc(const gg_plan_t* plan, const gg_model_desc_t* m, const int
   return GG_OK;
 }
 
+// size (floats) of parameter i of the offset table (include/gnnome_b200.h: gg_model_fwd)
+static int64_t param_floats(const ModelDims& m, int i) {
+  const int64_t d = m.d;
+  switch (i) {
+    case 0: return d * m.node_in;
+    case 1: return d;
+    case 2: return (int64_t)m.he * m.edge_in;
+    case 3: return m.he;
+    case 4: return d * m.he;
+    case 5: return d;
+    case 6: return (int64_t)m.H * 3 * d;
+    case 7: return m.H;
+    case 8: return m.H;
+    case 9: return 1;
+    default: break;
+  }
+  switch ((i - 10) % 8) {
+    case 0: return 5 * d * d;
+    case 1: return 5 * d;
+    case 2: return d * d;
+    default: return d;
+  }
+}
+
+// The gradient arena mirrors the parameter buffer.  When the table describes one span whose only gaps are alignment
+// padding (< 4 floats after a tensor: FlatLayout's always does) the whole span is zeroed with one memset at the start of
+// a pass; otherwise every op zeroes its own outputs as before.
+static bool arena_span(const ModelDims& m, const int64_t* offs, int n_offs, int64_t* lo, int64_t* floats) {
+  int64_t mn = INT64_MAX, mx = 0, sum = 0;
+  for (int i = 0; i < n_offs; ++i) {
+    const int64_t n = param_floats(m, i);
+    if (offs[i] < mn) mn = offs[i];
+    if (offs[i] + n > mx) mx = offs[i] + n;
+    sum += (n + 3) & ~3LL;
+  }
+  *lo = mn; *floats = mx - mn;
+  return n_offs > 0 && mx - mn <= sum && mx - mn > sum - 4;
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -217,9 +263,12 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   GG_TRY(gg_linear_fwd(dm.E, dm.he, dm.edge_k4, ws + w.e4, ws + w.W1e4, P(3), 1, ws + w.hid_e, stream));
   GG_TRY(gg_linear_fwd(dm.E, d, dm.he, ws + w.hid_e, P(4), P(5), 0, ws + w.e[0], stream));
   // L x GatedGCN                                                                           (processor.py:15-20)
+  if (w.stats_floats > 0) GG_CUDA(cudaMemsetAsync(ws + w.stats_all, 0, sizeof(float) * w.stats_floats, st));
+  struct Prezeroed { Prezeroed() { set_prezeroed(true); } ~Prezeroed() { set_prezeroed(false); } };
   for (int l = 0; l < dm.L; ++l) {
     const int o = 10 + 8 * l;
     set_layer_parity(l);                                  // zig-zag traversal: layer l starts where layer l-1 stopped
+    Prezeroed hint;
     GG_TRY(gg_layer_fwd(plan, d, m->norm_kind, 1, ws + w.h[l], ws + w.e[l], P(o), P(o + 1), P(o + 2), P(o + 3), P(o + 4),
                         P(o + 5), P(o + 6), P(o + 7), ws + w.h[l + 1], ws + w.e[l + 1], ws + w.P[l], ws + w.t[l],
                         ws + w.z[l], ws + w.agg[l], reinterpret_cast<double*>(ws + w.stats[l]), stream));
@@ -276,8 +325,15 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   const bool use_side = side != nullptr && side != st && L > 0 && !(gg_debug_flags_peek() & 128) && ev.init();   // bit 7: in line (A/B)
   bool (&pending)[2] = ev.pending;
   if (phase_begin <= 0) pending[0] = pending[1] = false;
+  int64_t arena_lo = 0, arena_floats = 0;
+  const bool one_memset = arena_span(dm, offs, n_offs, &arena_lo, &arena_floats);
+  struct Prezeroed { explicit Prezeroed(bool on) { set_prezeroed(on); } ~Prezeroed() { set_prezeroed(false); } } hint(one_memset);
   for (int ph = phase_begin < 0 ? 0 : phase_begin; ph < phase_end; ++ph) {
     if (ph == 0) {
+      if (one_memset) {                                   // every accumulator of the pass: two memsets instead of ~50
+        GG_CUDA(cudaMemsetAsync(grads + arena_lo, 0, sizeof(float) * arena_floats, st));
+        GG_CUDA(cudaMemsetAsync(bws + b.zero_begin, 0, sizeof(float) * (b.zero_end - b.zero_begin), st));
+      }
       GG_TRY(gg_gather_rows(dm.E, 1, g_scores, pl->perm, bws + b.g_int, stream));
       GG_TRY(gg_score_bwd(plan, d, dm.H, ws + w.h[L], ws + w.e[L], ws + w.Wq, ws + w.W1e, P(8), bws + b.g_int, ws + w.hid_s,
                           bws + b.g_h[0], bws + b.g_e[0], bws + b.dWq, bws + b.dbq, bws + b.dW1e, Gr(8), Gr(9),
@@ -299,7 +355,7 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
                                   reinterpret_cast<const double*>(ws + w.stats[l]), bws + b.g_h[in], bws + b.g_e[in],
                                   bws + b.g_h[out], bws + b.g_e[out], Gr(o), Gr(o + 1), Gr(o + 2), Gr(o + 3), Gr(o + 4),
                                   Gr(o + 5), Gr(o + 6), Gr(o + 7), bws + b.gP[k], bws + b.G, bws + b.g_eo, bws + b.g_t[k],
-                                  reinterpret_cast<double*>(bws + b.bstats), stream);
+                                  reinterpret_cast<double*>(bws + b.bstats + 2LL * 4 * d * l), stream);
       set_layer_bwd_side(nullptr, nullptr, nullptr);
       if (rc) return rc;
     } else {

@@ -193,7 +193,9 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
  * Workspaces are caller-owned: gg_model_workspace_floats(plan, m, which) floats, which = 0 forward that keeps what the
  * backward reads, 1 forward for inference (layer buffers reused), 2 backward scratch.  gg_model_bwd runs the phases
  * [phase_begin, phase_end) of: 0 predictor, 1 + k layer L-1-k, L + 1 encoders — a caller that all-reduces gradients
- * per layer issues one call per phase; 0 .. L + 2 does everything.
+ * per layer issues one call per phase; 0 .. L + 2 does everything.  A pass starts with phase 0: it zeroes every accumulator
+ * of the pass in two memsets (backward scratch + the span of `grads` the table covers, when the table's only gaps are
+ * alignment padding of < 4 floats; any other table makes each op zero its own outputs instead).
  * side_stream (may be NULL): a second caller-owned stream.  The weight-gradient GEMMs of every layer (dB3, dWn: nothing
  * downstream reads them) are forked onto it and joined back into `stream` by the call that runs the last phase, so
  * after a whole backward everything is ordered on `stream` as usual; a caller that consumes a layer's gradients between
