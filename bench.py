@@ -227,6 +227,7 @@ def run_ours(args):
 
     import gnnome_assembly_b200 as gg
     from gnnome_assembly_b200 import _lib
+    from gnnome_assembly_b200 import prep as gg_prep
     from gnnome_assembly_b200.dp import ArenaSync
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,10 +255,15 @@ def run_ours(args):
     # N > 1: per-layer-segment all-reduce of the flat gradient arena on a side stream, overlapped with the backward
     sync = ArenaSync(model) if world > 1 else None
     # train.py:210-211: criterion = BCEWithLogitsLoss(pos_weight=tensor([1 / pos_to_neg_ratio], device=device))
+    # Default: the engine's fused loss + TP/TN/FP/FN kernel (train.py:255,259-261 computes both every
+    # step), checked against torch's in tests/test_prep.py and against the oracle in the parity gate below.
+    # --torch-loss: torch's own criterion, as an unmodified train.py would call it.
     criterion = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([POS_WEIGHT], device=dev))
 
     def bce_loss(scores, y, _pw=None):
-        return criterion(scores.squeeze(-1), y)
+        if args.torch_loss:
+            return criterion(scores.squeeze(-1), y)
+        return gg_prep.bce_with_logits_and_metrics(scores, y, POS_WEIGHT)[0]
 
     graph = gg.AssemblyGraph(torch.from_numpy(g.src), torch.from_numpy(g.dst), N)
     gg.plan_for(graph, dev)                                    # plan creation excluded from timing (once per graph)
@@ -470,6 +476,8 @@ def run_ours(args):
                    "parallelism": f"dp{world} (independent graphs; NCCL all-reduce of the flat gradient arena per layer segment, "
                    "overlapped with the backward)" if world > 1 else "single GPU",
                    "cuda_graph": bool(use_graph),
+                   "loss": "torch.nn.BCEWithLogitsLoss(pos_weight)" if args.torch_loss else
+                   "engine's fused BCE-with-logits(pos_weight) + TP/TN/FP/FN kernel",
                    "l2": "512 MB memset between timed steps (outside the per-step event pairs); per-step working "
                    "set ~5 GB >> 126 MB L2"},
         "edge_layers_per_s": value * L,
@@ -507,6 +515,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / eager-CUDA baseline legs "
                     "(same-box A/B runs of library variants, tools/ab_bench.sh)")
+    ap.add_argument("--torch-loss", action="store_true", help="torch.nn.BCEWithLogitsLoss instead of the engine's fused "
+                    "loss + metrics kernel")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the first-step loss / gradient check against "
                     "the CPU oracle (about 15 s of host time)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel eagerly (default: the step "

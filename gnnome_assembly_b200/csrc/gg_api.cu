@@ -134,7 +134,7 @@ static int linear_bwd_weight(const char* tag, int64_t M, int N, int K, const flo
   EpiAtomic epi{dW, (int64_t)K};
   const int64_t m_tiles = (N + kBM - 1) / kBM;
   if (g_tc_mode && tc::eligible(true, true, N, K, M, lddy, ldx, dY, X)) {
-    const int64_t tiles = m_tiles * (K / tc::BN);
+    const int64_t tiles = m_tiles * ((K + tc::BN - 1) / tc::BN);
     // persistent CTAs, one work item (tile x split) at a time: the items must fit ONE wave.  Rounding the split count
     // up (5 tiles x 30 splits = 150 items on 148 SMs) made two CTAs run a second item while 146 idled: floor.
     int64_t want = sm_count() / tiles;

@@ -962,10 +962,12 @@ inline int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t o
   return GG_OK;
 }
 
-// K-major operands need K % 32 == 0 (whole 128-byte swizzle rows); MN-major ones take any K (zero fill)
+// K-major operands need K % 32 == 0 (whole 128-byte swizzle rows); MN-major ones take any K (zero fill).
+// N is a multiple of 64: a last n tile with 64 valid columns reads a zero-filled B box and its second epilogue group
+// never stores (d = 64: every layer GEMM is such a tile).
 inline bool eligible(bool a_mn, bool b_mn, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, const void* A,
                      const void* B) {
-  if (M <= 0 || K <= 0 || N % BN != 0 || lda % 4 != 0 || ldb % 4 != 0) return false;
+  if (M <= 0 || K <= 0 || N % 64 != 0 || lda % 4 != 0 || ldb % 4 != 0) return false;
   if ((!a_mn || !b_mn) && K % BK != 0) return false;
   if (a_mn && M % 4 != 0) return false;
   return (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0);

