@@ -276,3 +276,63 @@ def test_gradients_live_in_the_arena_and_survive_a_second_pass():
         assert model._gg_last_arena is not arena
         for k in first:
             assert torch.equal(first[k], kept[k])
+
+
+def test_model_abi_with_a_gapped_offset_table():
+    """include/gnnome_b200.h, gg_model_bwd: a table whose only gaps are alignment padding gets ONE memset of the whole
+    gradient span at phase 0; any other table (here: 64 floats between consecutive tensors) makes every op zero its own
+    outputs.  Both must give the same gradients, and the gapped call must not touch the gaps."""
+    dev = _dev()
+    import gnnome_assembly_b200 as gg
+    from gnnome_assembly_b200 import _lib, flat as gflat, functional as GF
+    from gnnome_assembly_b200.synth import make_assembly_graph
+    g = make_assembly_graph("chr19", seed=3, genome_len=1_500_000)
+    src, dst, e, pe, y = _graph_tensors(g)
+    graph = gg.AssemblyGraph(src, dst, g.num_nodes)
+    plan = gg.plan_for(graph, dev)
+    torch.manual_seed(1)
+    model = gg.GraphGatedGCNModel(1, 2, 128, 16, 2, 64, True, 16).to(dev)
+    layout = gflat.ensure_flat(model)
+    flatbuf = model.__dict__["_gg_flat"][1]
+    desc, offs, n = GF.model_call_table(model, layout)
+    C, lib = _lib.C, _lib.lib()
+    E = plan.num_edges
+    e_d, pe_d = e.to(dev), pe.to(dev)
+    g_scores = torch.randn(E, 1, device=dev) / E
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def run(params, table, grads):
+        ws = torch.empty(lib.gg_model_workspace_floats(plan.handle, C.byref(desc), 0), device=dev)
+        bws = torch.empty(lib.gg_model_workspace_floats(plan.handle, C.byref(desc), 2), device=dev)
+        scores = torch.empty(E, 1, device=dev)
+        tab = (C.c_int64 * n)(*table)
+        GF.check(lib.gg_model_fwd(plan.handle, C.byref(desc), GF.ptr(params), tab, n, GF.ptr(e_d), GF.ptr(pe_d), 1,
+                                  GF.ptr(ws), GF.ptr(scores), st), "gg_model_fwd")
+        GF.check(lib.gg_model_bwd(plan.handle, C.byref(desc), GF.ptr(params), tab, n, GF.ptr(g_scores), GF.ptr(ws),
+                                  GF.ptr(bws), GF.ptr(grads), 0, desc.layers + 2, st, None), "gg_model_bwd")
+        torch.cuda.synchronize()
+        return scores
+
+    packed = [int(offs[i]) for i in range(n)]
+    d, he, H = desc.d, desc.hidden_edge, desc.hidden_score
+    sizes = [d * desc.node_in, d, he * desc.edge_in, he, d * he, d, H * 3 * d, H, H, 1]        # the header's table
+    sizes += [5 * d * d, 5 * d, d * d, d, d, d, d, d] * desc.layers
+    gap, gapped, cur = 64, [0] * n, 64
+    for i in sorted(range(n), key=lambda i: packed[i]):
+        gapped[i] = cur
+        cur += sizes[i] + gap
+    flat2 = torch.zeros(cur, device=dev)
+    for i in range(n):
+        flat2[gapped[i]:gapped[i] + sizes[i]] = flatbuf[packed[i]:packed[i] + sizes[i]]
+    g1 = torch.full((layout.total,), 7.0, device=dev)
+    g2 = torch.full((cur,), 7.0, device=dev)
+    s1 = run(flatbuf, packed, g1)
+    s2 = run(flat2, gapped, g2)
+    assert torch.equal(s1, s2)
+    scale = float(g1.abs().max())
+    covered = torch.zeros(cur, dtype=torch.bool, device=dev)
+    for i in range(n):
+        a, b = g1[packed[i]:packed[i] + sizes[i]], g2[gapped[i]:gapped[i] + sizes[i]]
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, i   # split-K atomics reorder
+        covered[gapped[i]:gapped[i] + sizes[i]] = True
+    assert bool((g2[~covered] == 7.0).all())                   # the gaps belong to the caller

@@ -22,14 +22,14 @@ g = make_assembly_graph("chr19", seed=0, genome_len=int(CHR_LEN["chr19"] * scale
 torch.manual_seed(0)
 model = gg.GraphGatedGCNModel(1, 2, D, 16, L, 64, True, 16).to(dev)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([1 / 16.5], device=dev))
+from gnnome_assembly_b200.prep import bce_with_logits_and_metrics        # the bench step's loss (bench.py)
 graph = gg.AssemblyGraph(torch.from_numpy(g.src), torch.from_numpy(g.dst), g.num_nodes)
 e, pe, y = (torch.from_numpy(a).to(dev) for a in (g.e, g.pe, g.y))
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
 
 def step():
-    loss = crit(model(graph, None, e, pe).squeeze(-1), y)
+    loss = bce_with_logits_and_metrics(model(graph, None, e, pe), y, 1 / 16.5)[0]
     opt.zero_grad(set_to_none=True)
     loss.backward()
     opt.step()
