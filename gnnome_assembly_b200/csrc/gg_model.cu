@@ -171,6 +171,8 @@ static int check_desc(const gg_plan_t* plan, const gg_model_desc_t* m, const int
   }
   GG_REQUIRE(m->hidden_edge > 0 && m->hidden_edge % 4 == 0, "model: hidden_edge_features must be a multiple of 4");
   GG_REQUIRE(m->node_in > 0 && m->edge_in > 0, "model: bad input widths");
+  for (int i = 0; i < n_offs; ++i)      // float4 / TMA accesses: every tensor starts on a 16-byte boundary of the buffer
+    GG_REQUIRE(offs[i] >= 0 && offs[i] % 4 == 0, "model: every offset must be a non-negative multiple of 4 floats");
   const Plan* pl = reinterpret_cast<const Plan*>(plan);
   out->N = pl->N; out->E = pl->E;
   out->d = m->d; out->L = m->layers; out->he = m->hidden_edge; out->H = m->hidden_score;
@@ -246,6 +248,8 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   ModelDims dm;
   GG_TRY(check_desc(plan, m, offs, n_offs, &dm));
   GG_REQUIRE(params && ws, "model_fwd: null parameter buffer / workspace");
+  GG_REQUIRE(reinterpret_cast<uintptr_t>(params) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 16 == 0,
+             "model_fwd: parameter buffer / workspace must be 16-byte aligned");
   GG_REQUIRE(dm.E == 0 || (e && scores), "model_fwd: null edge input / output");
   GG_REQUIRE(dm.N == 0 || pe, "model_fwd: null node input");
   const Plan* pl = reinterpret_cast<const Plan*>(plan);
@@ -306,6 +310,9 @@ int gg_model_bwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   ModelDims dm;
   GG_TRY(check_desc(plan, m, offs, n_offs, &dm));
   GG_REQUIRE(params && ws && bws && grads, "model_bwd: null buffer");
+  GG_REQUIRE(reinterpret_cast<uintptr_t>(params) % 16 == 0 && reinterpret_cast<uintptr_t>(grads) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(ws) % 16 == 0 && reinterpret_cast<uintptr_t>(bws) % 16 == 0,
+             "model_bwd: parameter / gradient buffers and workspaces must be 16-byte aligned");
   GG_REQUIRE(dm.E == 0 || g_scores, "model_bwd: null upstream gradient");
   const Plan* pl = reinterpret_cast<const Plan*>(plan);
   cudaStream_t st = (cudaStream_t)stream;

@@ -188,6 +188,7 @@ int gg_score_bwd(const gg_plan_t* plan, int d, int H, const float* x, const floa
  *   5 .bias  6 predictor.W1.weight[H, 3d] 7 .bias  8 predictor.W2.weight[1, H] 9 .bias
  *   10 + 8 l + {0 Wn[5d, d] = A_1,A_2,A_3,B_1,B_2 stacked, 1 bn[5d], 2 B_3.weight, 3 B_3.bias, 4 bn_e.weight, 5 bn_e.bias,
  *               6 bn_h.weight, 7 bn_h.bias}
+ * Every offset is a multiple of 4 floats and both buffers are 16-byte aligned (vector and TMA accesses; GG_ERR_ARG otherwise).
  * `grads` (gg_model_bwd) is a flat buffer addressed by the SAME table.  e[E, edge_in], pe[N, node_in] and scores[E] are in
  * the CALLER's edge / node order (the permutation to the plan's internal order happens inside).
  * Workspaces are caller-owned: gg_model_workspace_floats(plan, m, which) floats, which = 0 forward that keeps what the

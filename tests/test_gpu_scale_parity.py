@@ -320,7 +320,7 @@ def test_model_abi_with_a_gapped_offset_table():
     gap, gapped, cur = 64, [0] * n, 64
     for i in sorted(range(n), key=lambda i: packed[i]):
         gapped[i] = cur
-        cur += sizes[i] + gap
+        cur += (sizes[i] + 3) // 4 * 4 + gap                    # every tensor on a 16-byte boundary (header contract)
     flat2 = torch.zeros(cur, device=dev)
     for i in range(n):
         flat2[gapped[i]:gapped[i] + sizes[i]] = flatbuf[packed[i]:packed[i] + sizes[i]]
@@ -336,3 +336,8 @@ def test_model_abi_with_a_gapped_offset_table():
         assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, i   # split-K atomics reorder
         covered[gapped[i]:gapped[i] + sizes[i]] = True
     assert bool((g2[~covered] == 7.0).all())                   # the gaps belong to the caller
+    # a table that breaks the alignment contract is refused, not executed
+    bad = list(gapped)
+    bad[1] += 1
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        run(flat2, bad, g2)
