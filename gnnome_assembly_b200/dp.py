@@ -175,7 +175,11 @@ class ArenaSync:
             if not p.requires_grad:
                 continue
             if p.grad is None or p.grad.data_ptr() != base + 4 * off:
-                if p.grad is not None and p.grad.data_ptr() != base + 4 * off:
+                # Autograd normally ADOPTS the arena view as .grad (no copy).  If the gradients were unset when the
+                # backward started and .grad is still somewhere else, autograd made a private copy instead (seen under
+                # compute-sanitizer): the copy holds this rank's un-reduced values, the arena holds the mean — re-point.
+                # A .grad that existed BEFORE the backward was accumulated into and cannot be replaced: refuse.
+                if p.grad is not None and not arena.grads_unset_at_backward:
                     raise RuntimeError("ArenaSync: a gradient does not live in the pass's arena — call "
                                        "optimizer.zero_grad(set_to_none=True) before backward")
                 p.grad = buf[off:off + p.numel()].view_as(p)

@@ -69,10 +69,12 @@ class GradArena:
         self.layout, self.device = layout, device
         self.buf = None
         self.on_segment_ready = None             # callable(offset, size): dp.OverlappedGradSync hooks in here
+        self.grads_unset_at_backward = None      # were all .grad None when the backward started (see dp.ArenaSync.finish)
 
     def tensor(self):
         if self.buf is None:
             self.buf = torch.empty(self.layout.total, device=self.device, dtype=torch.float32)
+            self.grads_unset_at_backward = all(p.grad is None for p, _ in self.layout.entries)
         return self.buf
 
     def slot(self, param, rows=None):

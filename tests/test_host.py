@@ -202,7 +202,37 @@ def _arena_worker(rank, world, port, q):
     else:
         sync.idle_step()
     b = [float(p.grad.flatten()[0]) for p in model.parameters()]
-    q.put((rank, a, b))
+    # autograd made private copies instead of adopting the arena views (seen under compute-sanitizer): the copies hold
+    # the local values, the arena the mean -> finish() re-points .grad into the arena
+    sync.begin(world)
+    for p in model.parameters():
+        p.grad = None
+    arena = GradArena(layout, torch.device("cpu"))
+    model.arena_hook(arena)
+    arena.tensor().fill_(float(10 * (rank + 1)))
+    for p, off in layout.entries:
+        p.grad = arena.tensor()[off:off + p.numel()].view_as(p).clone()
+    arena.segment_done("conv1")
+    arena.segment_done("conv0")
+    sync.finish()
+    base = arena.tensor().data_ptr()
+    assert all(p.grad.data_ptr() == base + 4 * off for p, off in layout.entries)
+    c = [float(p.grad.flatten()[0]) for p in model.parameters()]
+    # ... but a .grad that existed before the backward (accumulation) cannot be replaced: loud error, on every rank
+    sync.begin(world)
+    arena = GradArena(layout, torch.device("cpu"))
+    model.arena_hook(arena)
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    arena.tensor().fill_(1.0)
+    arena.segment_done("conv1")
+    arena.segment_done("conv0")
+    try:
+        sync.finish()
+        refused = False
+    except RuntimeError as err:
+        refused = "zero_grad" in str(err)
+    q.put((rank, a, b, c, refused))
     dist.destroy_process_group()
 
 
@@ -219,9 +249,11 @@ def test_arena_sync_gloo_world2():
     res = [q.get(timeout=180) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for _, a, b in res:
+    for _, a, b, c, refused in res:
         assert all(abs(x - 1.5) < 1e-6 for x in a) and len(a) == 42          # mean of 1 and 2, every parameter
         assert all(abs(x - 5.0) < 1e-6 for x in b)                           # rank 0's gradient alone, on both ranks
+        assert all(abs(x - 15.0) < 1e-6 for x in c)                          # copied gradients re-pointed to the mean
+        assert refused
 
 
 def test_flat_parameters_keep_the_reference_state_dict():
