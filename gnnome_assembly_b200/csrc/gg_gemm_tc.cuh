@@ -291,7 +291,7 @@ struct BnBwdATx {
 };
 
 // ---------------------------------------------------------------------------------- the kernel
-template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx, bool kWRes = false>
+template <bool A_MN, bool B_MN, bool kStats, bool kBiasGrad, class Epi, class ATx, bool kWRes = false, bool kNarrow = false>
 __global__ void __launch_bounds__(threads<ATx>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmOut2, Args g, Epi epi, ATx atx) {
@@ -712,6 +712,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4* stg = reinterpret_cast<float4*>(staging) + grp * (BM * EC / 4);
     int* idx_base = sidx + grp * 4 * BM;                // [2 buffers][src | dst][128]
     const int tcol = tg % TPR, trow = tg / TPR;             // this thread's float4 column / row inside a pass
+    // N <= 64 with chunks narrower than 64 columns (d = 64): the two groups share the 64 valid columns, 32 each, instead
+    // of group 1 idling.  (64-column chunks — the score predictor's wide staging — keep the idle group below.)
+    // (kNarrow is chosen by launch(): a compile-time switch, so the N = 128 kernels are the code they were.)
+    static_assert(!kNarrow || QN >= 2, "narrow mode needs chunks of at most 32 columns");
+    constexpr bool narrow = kNarrow;
+    auto cbase = [&]() { return narrow ? 32 * grp : 64 * grp; };   // first accumulator column of this group (re-derived at
+                                                                  // each use: a live variable changed the N = 128 kernels' allocation)
+    constexpr int qn = narrow ? QN / 2 : QN;              // chunks this group walks per tile
     const int c4 = tcol * 4;                              // column offset of this thread inside a chunk
     auto swz = [](int row) { return EC == 16 ? ((row >> 1) & 3) : (row & (TPR - 1)); };   // staging xor-swizzle
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
@@ -729,7 +737,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int64_t m = (int64_t)mt_ * BM + p * RPP + trow;
       return m < g.M ? m : g.M - 1;
     };
-    auto col_of = [&](int nt_, int q) { return nt_ * BN + 64 * grp + EC * q + c4; };
+    auto col_of = [&](int nt_, int q) { return nt_ * BN + cbase() + EC * q + c4; };
     auto fetch_tile = [&](int mt_, int nt_, int buf) {
       if (g.dbg & 2) return;
 #pragma unroll
@@ -740,8 +748,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t m = row_of(mt_, p);
 #pragma unroll
         for (int q = 0; q < QN; ++q) {
-          epi.prefetch_deep(deep[q][p], m, col_of(nt_, q), sv, dv);
-          epi.prefetch_near(near[q][p], m, col_of(nt_, q), sv, dv);
+          if (q < qn) {
+            epi.prefetch_deep(deep[q][p], m, col_of(nt_, q), sv, dv);
+            epi.prefetch_near(near[q][p], m, col_of(nt_, q), sv, dv);
+          }
         }
       }
     };
@@ -764,7 +774,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_ph = 0;
     int cur = 0;                                        // idx buffer of the current tile
     int64_t w = blockIdx.x;
-    if (g.n_tiles == 1 && 64 * grp >= g.N) {
+    if (!narrow && g.n_tiles == 1 && 64 * grp >= g.N) {
       // N <= 64 (the score predictor's hidden layer): this group's 64 columns are never valid.  It only hands the
       // accumulators back; its group barriers, staging and idx buffers are its own, so skipping them is consistent.
       for (; w < total_work; w += gridDim.x) {
@@ -799,6 +809,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m0 = (int64_t)mt * BM;
 #pragma unroll
       for (int q = 0; q < QN; ++q) {
+        if constexpr (narrow) { if (q >= qn) break; }
         if constexpr (!kHeavyEpi) {
           // all of the chunk's TMEM loads are issued before the first wait (one round trip instead of EC / 16).  Only
           // for epilogues without a tile of prefetched operands in registers: with them (edge gate: 128 registers of
@@ -806,10 +817,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[EC / 16][16];
 #pragma unroll
           for (int sub = 0; sub < EC / 16; ++sub)
-            tmem_ld16_issue(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v[sub]);
+            tmem_ld16_issue(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + cbase() + EC * q + 16 * sub), v[sub]);
 #pragma unroll
           for (int sub = 0; sub < EC / 16; ++sub) tmem_ld16_fence(v[sub]);
-          if (q == QN - 1) {                            // accumulator fully read: hand it back to the MMA warp
+          if (q == qn - 1) {                            // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
           }
@@ -824,8 +835,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int sub = 0; sub < EC / 16; ++sub) {
             float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + 64 * grp + EC * q + 16 * sub), v);
-            if (q == QN - 1 && sub == EC / 16 - 1) {    // accumulator fully read: hand it back to the MMA warp
+            tmem_ld16(tmem_base + ((uint32_t)(32 * ew) << 16) + (uint32_t)(acc * BN + cbase() + EC * q + 16 * sub), v);
+            if (q == qn - 1 && sub == EC / 16 - 1) {    // accumulator fully read: hand it back to the MMA warp
               tc_fence_before();
               mbar_arrive(tmem_empty(acc));
             }
@@ -876,8 +887,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane < TPR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 0] += (double)s1[j];
-              sstat[(ew * BN + 64 * grp + EC * q + c4 + j) * 2 + 1] += (double)s2[j];
+              sstat[(ew * BN + cbase() + EC * q + c4 + j) * 2 + 0] += (double)s1[j];
+              sstat[(ew * BN + cbase() + EC * q + c4 + j) * 2 + 1] += (double)s2[j];
             }
           }
         }
@@ -885,8 +896,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if constexpr (kStats) {
         // flush this tile's column statistics (the n tile can change between work items)
-        const int col = 64 * grp + (tg & 63);
-        if (tg < 64) {
+        const int col = narrow ? 32 * grp + (tg & 31) : 64 * grp + (tg & 63);
+        if (tg < (narrow ? 32 : 64)) {
           double a = 0.0, b = 0.0;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) { a += sstat[(qq * BN + col) * 2]; b += sstat[(qq * BN + col) * 2 + 1]; }
@@ -1019,19 +1030,28 @@ int launch(const char* tag, const float* A, int64_t lda, const float* B, int64_t
     set_error("gnnome_b200: W-resident GEMM needs one n tile, K <= 128, no split-K");
     return GG_ERR_UNSUPPORTED;
   }
-  auto kern = gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx, kWRes>;
   constexpr int kSmem = smem_bytes<kStats, Epi, ATx, kWRes>();
   static_assert(kSmem <= 227 * 1024, "shared-memory layout exceeds 227 KB");
-  static bool attr_set_dev[kMaxDevices] = {};      // one static per template instantiation, per device
-  bool& attr_set = attr_set_dev[current_device()];
-  if (!attr_set) {
-    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
+  // N <= 64 (every layer GEMM at d = 64): the variant whose two epilogue groups share the 64 valid columns.  A separate
+  // instantiation, so the N = 128 kernels keep their code (and register allocation) to the instruction.
+  constexpr bool kCanNarrow = Cfg<ATx, Epi, kWRes>::kEC <= 32;
+  const bool narrow = kCanNarrow && g.n_tiles == 1 && N <= 64;
+  auto launch_variant = [&](auto kern, bool& attr_set) -> int {
+    if (!attr_set) {
+      GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      attr_set = true;
+    }
+    GG_KERNEL_BEGIN(tag, st);
+    kern<<<grid, threads<ATx>(), kSmem, st>>>(tmA, tmB, tmA2, tmOut2, g, epi, atx);
+    GG_KERNEL_END(tag, st);
+    return GG_OK;
+  };
+  static bool attr_set_dev[2][kMaxDevices] = {};   // one static per template instantiation: [narrow][device]
+  if constexpr (kCanNarrow) {
+    if (narrow)
+      return launch_variant(gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx, kWRes, true>, attr_set_dev[1][current_device()]);
   }
-  GG_KERNEL_BEGIN(tag, st);
-  kern<<<grid, threads<ATx>(), kSmem, st>>>(tmA, tmB, tmA2, tmOut2, g, epi, atx);
-  GG_KERNEL_END(tag, st);
-  return GG_OK;
+  return launch_variant(gemm_tc_kernel<A_MN, B_MN, kStats, kBiasGrad, Epi, ATx, kWRes, false>, attr_set_dev[0][current_device()]);
 }
 
 }  // namespace tc
