@@ -57,6 +57,7 @@ SIGNATURES = {
     "gg_bce_bwd": (_i, [_i64, _p, _p, C.c_float, _p, _p, _p]),
     "gg_gather_rows": (_i, [_i64, _i, _p, _p, _p, _p]),
     "gg_edge_mlp_bwd": (_i, [_i64, _i, _i, _i] + [_p] * 9),
+    "gg_edge_mlp_fwd": (_i, [_i64, _i, _i, _i] + [_p] * 8),
     "gg_decode_walks": (_i, [_i64] + [_p] * 10 + [_i] + [_p] * 10),
     "gg_decode_commit": (_i, [_i64, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
     "gg_decode_edge_weights": (_i, [_i64, _p, _p, _p, _p, _p, _p]),

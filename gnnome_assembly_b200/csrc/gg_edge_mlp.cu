@@ -1,5 +1,5 @@
-// gg_edge_mlp.cu — backward of the edge encoder  e0 = W2 relu(W1 e + b1) + b2  (models/full_graph.py:17-18,24-26)
-// in ONE pass over the E x d gradient.
+// gg_edge_mlp.cu — the edge encoder  e0 = W2 relu(W1 e + b1) + b2  (models/full_graph.py:17-18,24-26): its backward
+// in ONE pass over the E x d gradient, and (below) its forward in one pass as well.
 //
 // As three GEMM calls (dW2 = g^T hid, g_hid = (g W2) [hid > 0], dW1 = g_hid^T e) the E x d gradient is read
 // twice by narrow-N FFMA kernels (N = 16) that run far from both rooflines (150 + 200 us on the chr19 graph,
@@ -147,9 +147,116 @@ edge_mlp_bwd_kernel(int64_t E, const float* __restrict__ g, const float* __restr
   }
 }
 
+
+// Forward of the same encoder in one pass: hid = relu(W1 e + b1) [E, 16], out = W2 hid + b2 [E, d].  As two GEMM calls
+// (N = 16 and K = 16: FFMA kernels, 29 + 83 us on the chr19 graph) the E x 16 intermediate is written and re-read and
+// the second call runs at a third of the write bandwidth.  Here a warp owns 32 CONSECUTIVE rows at a time: lane i loads
+// row i's (padded) features with one coalesced access and computes that row's 16 hidden units (W1 / b1 are shared-memory
+// broadcasts), stores them as one contiguous 2 KB block, and then the warp walks the 32 rows: the row's hidden units
+// are broadcast from lane i (16 shuffles) into the W2 rows every lane keeps in registers for its Row<D> channels.  The
+// next block's features are requested before the current one is processed.  (A first version that gave every warp
+// single rows in a grid-stride loop paid a DRAM round trip per row pair: 136 us, slower than the two GEMMs.)
+template <int D>
+__global__ void __launch_bounds__(kMlpThreads, 2)
+edge_mlp_fwd_kernel(int64_t E, const float* __restrict__ e, const float* __restrict__ W1, const float* __restrict__ b1,
+                    const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ hid,
+                    float* __restrict__ out) {
+  constexpr int VPL = D / 32, H = kMlpHid;
+  __shared__ float4 sw1[H];
+  __shared__ float sb1[H];
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * kMlpThreads + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * kMlpThreads) >> 5;
+  if (threadIdx.x < H) {
+    sw1[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(W1) + threadIdx.x);   // W1[k][0..3] (K padded to 4 with zeros)
+    sb1[threadIdx.x] = __ldg(b1 + threadIdx.x);
+  }
+  __syncthreads();
+  float w2[VPL][H], bo[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = Row<D>::channel(i, lane);
+    bo[i] = __ldg(b2 + c);
+#pragma unroll
+    for (int k = 0; k < H / 4; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(W2 + (int64_t)c * H) + k);
+      w2[i][4 * k] = t.x; w2[i][4 * k + 1] = t.y; w2[i][4 * k + 2] = t.z; w2[i][4 * k + 3] = t.w;
+    }
+  }
+  const int64_t blocks32 = (E + 31) / 32;
+  auto fetch = [&](int64_t blk) {
+    const int64_t r = blk * 32 + lane;
+    return (blk < blocks32 && r < E) ? __ldg(reinterpret_cast<const float4*>(e) + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 xn = fetch(gw);
+  for (int64_t blk = gw; blk < blocks32; blk += nw) {
+    const float4 x = xn;
+    xn = fetch(blk + nw);
+    const int64_t base = blk * 32;
+    const int rows = (int)(E - base < 32 ? E - base : 32);
+    float h[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {                            // same order as the GEMM path: sum over k, then the bias
+      const float4 w = sw1[k];
+      h[k] = fmaxf(fmaf(x.w, w.w, fmaf(x.z, w.z, fmaf(x.y, w.y, x.x * w.x))) + sb1[k], 0.f);
+    }
+    if (lane < rows) {
+      float4* hp = reinterpret_cast<float4*>(hid + (base + lane) * H);
+#pragma unroll
+      for (int k = 0; k < H / 4; ++k) hp[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+    }
+    for (int j = 0; j < rows; j += 2) {                      // two rows per step: independent shuffle / FMA chains
+      const int j1 = j + 1 < rows ? j + 1 : j;
+      Row<D> o0, o1;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) { o0.v[i] = 0.f; o1.v[i] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const float a0 = __shfl_sync(0xffffffffu, h[k], j), a1 = __shfl_sync(0xffffffffu, h[k], j1);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          o0.v[i] = fmaf(a0, w2[i][k], o0.v[i]);
+          o1.v[i] = fmaf(a1, w2[i][k], o1.v[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) { o0.v[i] += bo[i]; o1.v[i] += bo[i]; }
+      o0.store(out + (base + j) * D, lane);
+      if (j + 1 < rows) o1.store(out + (base + j + 1) * D, lane);
+    }
+  }
+}
+
 }  // namespace gg
 
 using namespace gg;
+
+extern "C" int gg_edge_mlp_fwd(int64_t E, int d, int hidden, int K, const float* e, const float* W1, const float* b1,
+                               const float* W2, const float* b2, float* hid, float* out, void* stream) {
+  GG_REQUIRE(E >= 0, "edge_mlp_fwd: negative size");
+  if (hidden != kMlpHid || K != kMlpK || !(d == 64 || d == 128)) {
+    set_error("gnnome_b200: edge_mlp_fwd is built for hidden_edge_features = 16, K = 4 (2 padded), d in {64,128}");
+    return GG_ERR_UNSUPPORTED;
+  }
+  GG_REQUIRE(W1 && b1 && W2 && b2, "edge_mlp_fwd: null parameter");
+  GG_REQUIRE(E == 0 || (e && hid && out), "edge_mlp_fwd: null edge buffer");
+  GG_REQUIRE(reinterpret_cast<uintptr_t>(e) % 16 == 0 && reinterpret_cast<uintptr_t>(W1) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(W2) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(hid) % 16 == 0,
+             "edge_mlp_fwd: e, W1, W2, hid and out must be 16-byte aligned");
+  if (E == 0) return GG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  int64_t blocks = (E + 255) / 256;                           // 8 warps x 32 rows per CTA and iteration
+  if (blocks > 2LL * sms) blocks = 2LL * sms;
+  GG_KERNEL_BEGIN("edge_mlp_fwd_kernel", st);
+  if (d == 64) edge_mlp_fwd_kernel<64><<<(unsigned)blocks, kMlpThreads, 0, st>>>(E, e, W1, b1, W2, b2, hid, out);
+  else edge_mlp_fwd_kernel<128><<<(unsigned)blocks, kMlpThreads, 0, st>>>(E, e, W1, b1, W2, b2, hid, out);
+  GG_KERNEL_END("edge_mlp_fwd_kernel", st);
+  return GG_OK;
+}
 
 extern "C" int gg_edge_mlp_bwd(int64_t E, int d, int hidden, int K, const float* g, const float* hid, const float* e,
                                const float* W2, float* dW1, float* db1, float* dW2, float* db2, void* stream) {

@@ -264,8 +264,16 @@ int gg_model_fwd(const gg_plan_t* plan, const gg_model_desc_t* m, const float* p
   GG_TRY(copy_rows("pad_weight_kernel", dm.he, dm.edge_in, dm.edge_k4, P(2), nullptr, ws + w.W1e4, st));
   // encoders                                                                               (full_graph.py:23-26)
   GG_TRY(gg_linear_fwd(dm.N, d, dm.node_k4, ws + w.pe4, ws + w.Wpe4, P(1), 0, ws + w.h[0], stream));
-  GG_TRY(gg_linear_fwd(dm.E, dm.he, dm.edge_k4, ws + w.e4, ws + w.W1e4, P(3), 1, ws + w.hid_e, stream));
-  GG_TRY(gg_linear_fwd(dm.E, d, dm.he, ws + w.hid_e, P(4), P(5), 0, ws + w.e[0], stream));
+  {
+    int rc = gg_edge_mlp_fwd(dm.E, d, dm.he, dm.edge_k4, ws + w.e4, ws + w.W1e4, P(3), P(4), P(5), ws + w.hid_e, ws + w.e[0],
+                             stream);
+    if (rc == GG_ERR_UNSUPPORTED) {                         // other widths: the two layers as two GEMM calls
+      GG_TRY(gg_linear_fwd(dm.E, dm.he, dm.edge_k4, ws + w.e4, ws + w.W1e4, P(3), 1, ws + w.hid_e, stream));
+      GG_TRY(gg_linear_fwd(dm.E, d, dm.he, ws + w.hid_e, P(4), P(5), 0, ws + w.e[0], stream));
+    } else if (rc) {
+      return rc;
+    }
+  }
   // L x GatedGCN                                                                           (processor.py:15-20)
   if (w.stats_floats > 0) GG_CUDA(cudaMemsetAsync(ws + w.stats_all, 0, sizeof(float) * w.stats_floats, st));
   struct Prezeroed { Prezeroed() { set_prezeroed(true); } ~Prezeroed() { set_prezeroed(false); } };

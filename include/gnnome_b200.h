@@ -249,6 +249,11 @@ int gg_gather_rows(int64_t rows, int width, const float* in, const int32_t* idx,
  * GG_ERR_UNSUPPORTED and the caller uses gg_linear_bwd_weight / gg_linear_bwd_data.  Outputs are zeroed here. */
 int gg_edge_mlp_bwd(int64_t E, int d, int hidden, int K, const float* g, const float* hid, const float* e,
                     const float* W2, float* dW1, float* db1, float* dW2, float* db2, void* stream);
+/* The forward of the same two layers (models/full_graph.py:24-26) in one pass: hid[E,hidden] = relu(W1 e + b1) (kept for
+ * the backward), out[E,d] = W2 hid + b2.  e[E,K] zero-padded raw edge features, W1[hidden,K] padded alike.  Same shape
+ * limits and fallback (two gg_linear_fwd calls) as gg_edge_mlp_bwd; e, W1, W2, hid, out 16-byte aligned. */
+int gg_edge_mlp_fwd(int64_t E, int d, int hidden, int K, const float* e, const float* W1, const float* b1,
+                    const float* W2, const float* b2, float* hid, float* out, void* stream);
 
 /* ---- greedy contig decoding -------------------------------------------------------------------
  * Replaces the body of get_contigs (inference.py:182-259): per decoding iteration the reference samples

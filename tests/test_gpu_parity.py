@@ -183,6 +183,45 @@ def test_linear_unpadded_k():
         assert _oracle().rel_err(lin.weight.grad, x.double().sum(0).expand(N, K)) < 1e-5
 
 
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("E", [0, 1, 17, 4097, 100_003])
+def test_edge_encoder_forward_one_pass(d, E):
+    """gg_edge_mlp_fwd (models/full_graph.py:24-26 in one kernel) against the same two layers in fp64: the hidden
+    activations it keeps for the backward and the encoder output; odd row counts exercise the two-rows-per-warp tail."""
+    dev = _dev()
+    from gnnome_assembly_b200 import _lib
+    from gnnome_assembly_b200._lib import check, ptr
+    torch.manual_seed(E + d)
+    l1, l2 = torch.nn.Linear(2, 16).to(dev), torch.nn.Linear(16, d).to(dev)
+    e = torch.randn(E, 2, device=dev)
+    e4 = torch.zeros(E, 4, device=dev)
+    e4[:, :2] = e
+    W1 = torch.zeros(16, 4, device=dev)
+    W1[:, :2] = l1.weight.detach()
+    hid = torch.full((E, 16), -7.0, device=dev)
+    out = torch.full((E, d), -7.0, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    check(_lib.lib().gg_edge_mlp_fwd(E, d, 16, 4, ptr(e4), ptr(W1), ptr(l1.bias.detach()), ptr(l2.weight.detach()),
+                                     ptr(l2.bias.detach()), ptr(hid), ptr(out), st), "gg_edge_mlp_fwd")
+    torch.cuda.synchronize()
+    if E == 0:
+        return
+    h64 = torch.relu(torch.nn.functional.linear(e.double(), l1.weight.double(), l1.bias.double()))
+    o64 = torch.nn.functional.linear(h64, l2.weight.double(), l2.bias.double())
+    assert _oracle().rel_err(hid, h64) < 1e-6
+    assert _oracle().rel_err(out, o64) < 1e-6
+
+
+def test_edge_encoder_forward_other_shapes_are_refused():
+    dev = _dev()
+    from gnnome_assembly_b200 import _lib
+    from gnnome_assembly_b200._lib import ptr
+    x = torch.zeros(64, 256, device=dev)
+    rc = _lib.lib().gg_edge_mlp_fwd(4, 256, 16, 4, ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x),
+                                    torch.cuda.current_stream(dev).cuda_stream)
+    assert rc != 0 and b"edge_mlp_fwd" in _lib.lib().gg_last_error()     # the sequencer falls back to two GEMM calls
+
+
 # ------------------------------------------------------------------------------------------ layer
 def _rand_graph(n, m, seed, isolated=0.1):
     from gnnome_assembly_b200.synth import make_random_graph
