@@ -32,6 +32,17 @@ def test_sass_is_sm100a():
     assert "sm_100a" in out.stdout
 
 
+def test_sass_uses_tcgen05_tmem_and_tma():
+    """The shipped library is Blackwell-native where it claims to be: the GEMM kernels issue tcgen05 MMAs
+    (UTCHMMA) with TMEM loads / stores (LDTM / STTM), operands arrive through TMA tensor loads (UTMALDG), the fused
+    g_t tile leaves through a TMA tensor store (UTMASTG); `profiles/r2_sass_summary.txt` is the per-kernel table."""
+    import subprocess
+    from gnnome_assembly_b200 import _lib
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "USETMAXREG"):
+        assert mnemonic in sass, f"no {mnemonic} in the library's SASS"
+
+
 def test_package_surface_matches_reference():
     import gnnome_assembly_b200 as gg
     for name in ("GatedGCN_1d", "GraphGatedGCN", "ScorePredictor", "NodeEncoder", "EdgeEncoder"):
