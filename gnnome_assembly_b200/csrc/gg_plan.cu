@@ -79,7 +79,7 @@ using gg::Plan;
 
 extern "C" {
 
-int gg_version(void) { return 100; }
+int gg_version(void) { return 200; }   // 100: round-1 ABI; 200: + gg_model_*, gg_edge_mlp_fwd, device-built plans, plan flags
 
 const char* gg_last_error(void) { return gg::last_error_cstr(); }
 

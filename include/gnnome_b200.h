@@ -30,7 +30,7 @@ extern "C" {
 
 typedef struct gg_plan gg_plan_t;
 
-int gg_version(void);
+int gg_version(void);          /* 100 = round-1 entry points; 200 = + whole-model calls, gg_edge_mlp_fwd, plan flags (a superset) */
 const char* gg_last_error(void);
 
 /* ---- instrumentation ------------------------------------------------------------------------
