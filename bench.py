@@ -305,7 +305,7 @@ def run_ours(args):
         parity = {"first_step_loss": float(loss0.detach()), "oracle_loss": float(ref0.detach()), "abs_diff": abs(float(loss0.detach()) - float(ref0.detach())),
                   "grad_tensors_checked": len(list(oracle.parameters())), "grad_mismatches": len(bad),
                   "tolerance": "loss 1e-5 relative; gradients rtol 2e-3 of each tensor's max + 1e-5 of the model's max"}
-        assert parity["abs_diff"] < 1e-5 * max(1.0, abs(float(ref0))), f"bench: first-step loss differs from the oracle: {parity}"
+        assert parity["abs_diff"] < 1e-5 * max(1.0, abs(float(ref0.detach()))), f"bench: first-step loss differs from the oracle: {parity}"
         assert not bad, f"bench: gradients differ from the oracle: {bad[:3]}"
         del oracle, twin, loss0
         torch.cuda.synchronize()

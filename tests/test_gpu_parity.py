@@ -479,7 +479,7 @@ def test_full_size_training_step_finite_and_decreasing(chr19_graph):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
 
 

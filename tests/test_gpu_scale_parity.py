@@ -80,7 +80,7 @@ def test_chr19_size_gradients_tc_path(chr19_graph):
     model, oracle = _model_pair(128, 2, dev)
     s, loss, r, rloss = _fwd_bwd_both(model, oracle, g, dev)
     assert rel_err(s, r) < TOL
-    assert abs(float(loss) - float(rloss)) < 1e-5 * max(1.0, abs(float(rloss)))
+    assert abs(float(loss.detach()) - float(rloss.detach())) < 1e-5 * max(1.0, abs(float(rloss.detach())))
     bad = grads_close({k: p.grad for k, p in model.named_parameters()},
                       {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5)
     assert bad == [], bad[:4]
@@ -146,7 +146,7 @@ def test_config5_point_1m_edges_d256():
     model, oracle = _model_pair(256, 1, dev, seed=5)
     s, loss, r, rloss = _fwd_bwd_both(model, oracle, g, dev)
     assert rel_err(s, r) < TOL
-    assert abs(float(loss) - float(rloss)) < 1e-5 * max(1.0, abs(float(rloss)))
+    assert abs(float(loss.detach()) - float(rloss.detach())) < 1e-5 * max(1.0, abs(float(rloss.detach())))
     bad = grads_close({k: p.grad for k, p in model.named_parameters()},
                       {k: p.grad for k, p in oracle.named_parameters()}, rtol=2e-3, atol_frac=1e-5)
     assert bad == [], bad[:4]
@@ -200,7 +200,7 @@ def test_training_trajectory_tc_equals_ffma(chr19_graph):
                 opt.zero_grad()
                 loss.backward()
                 opt.step()
-                out.append(float(loss))
+                out.append(float(loss.detach()))
             return out
         finally:
             _lib.set_tc_mode(old)
